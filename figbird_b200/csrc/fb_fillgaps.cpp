@@ -1,0 +1,272 @@
+// fb_fillgaps.cpp -- fb_fillgaps_main(): the drop-in for the `FillGaps` executable.
+//
+// Same 15 positional arguments, same input files, same output files as FillGaps.cpp:371-947 + the worker
+// processes it spawns (Figbird.cpp main :6909-7508).  What is different by design:
+//   * no worker processes, no run-time compilation: the model is learned once, gaps are sharded
+//     cost-balanced over the visible GPUs (FIGBIRD_GPUS), one engine context per GPU, no collective;
+//   * every gap runs its sequential control logic on a host thread; the device requests of all gaps in
+//     flight on a GPU are merged into one fb_em_run per tick (BatchQueue below);
+//   * draw.txt is written in gap order (the reference concatenates it in worker order, FillGaps.cpp:222-258).
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <thread>
+
+#include "fb_gapfiller.h"
+#include "fb_io.h"
+
+namespace fb {
+
+// Merges the requests of all gap threads that are currently blocked into one engine call.  The last
+// thread to block (or to leave) runs the flush; nobody else is runnable at that moment.
+class BatchQueue : public DeviceQueue {
+public:
+    BatchQueue(fb_ctx* ctx, int workers) : ctx_(ctx), running_(workers) {}
+    void submit(int gapIdx, const std::vector<ItemSpec>& items, std::vector<ItemResult>& results) override {
+        Req rq{gapIdx, &items, &results, false};
+        std::unique_lock<std::mutex> lk(mu_);
+        reqs_.push_back(&rq);
+        if ((int)reqs_.size() >= running_) flush(lk);
+        else cv_.wait(lk, [&] { return rq.done; });
+        if (failed_) throw std::runtime_error(err_);
+    }
+    void workerExit() {
+        std::unique_lock<std::mutex> lk(mu_);
+        running_--;
+        if (!reqs_.empty() && (int)reqs_.size() >= running_) flush(lk);
+    }
+    int64_t ticks() const { return ticks_; }
+
+private:
+    struct Req { int gap; const std::vector<ItemSpec>* items; std::vector<ItemResult>* results; bool done; };
+    void flush(std::unique_lock<std::mutex>&) {
+        std::vector<Req*> batch; batch.swap(reqs_);
+        std::vector<FbWorkItem> wi;
+        for (Req* r : batch) for (const ItemSpec& s : *r->items) {
+            FbWorkItem w{}; w.kind = s.kind; w.gap = r->gap; w.cand_len = s.candLen; w.max_rounds = s.maxRounds; w.flags = s.flags;
+            w.comp_count_in = s.compIn; w.counts_in = s.countsIn.empty() ? nullptr : s.countsIn.data();
+            w.string_in = s.stringIn.empty() ? nullptr : s.stringIn.data();
+            wi.push_back(w);
+        }
+        std::vector<const FbItemOut*> outs(wi.size(), nullptr);
+        fb_status st = wi.empty() ? FB_OK : fb_em_run(ctx_, wi.data(), (int32_t)wi.size(), outs.data());
+        ticks_++;
+        if (st != FB_OK) { failed_ = true; err_ = std::string("fb_em_run failed: ") + fb_last_error(ctx_); }
+        size_t k = 0;
+        for (Req* r : batch) {
+            r->results->clear();
+            for (size_t i = 0; i < r->items->size(); i++, k++) {
+                ItemResult res;
+                if (!failed_) {
+                    const FbItemOut* h = outs[k]; const unsigned char* b = (const unsigned char*)h;
+                    res.calls = h->calls; res.compCount = h->comp_count; res.flags = h->flags; res.nReads = h->n_reads;
+                    res.candLen = h->cand_len; res.nSlots = h->n_slots; res.placements = h->placements;
+                    const size_t n = (size_t)h->n_slots * h->n_reads;
+                    const double* p1 = (const double*)(b + h->off_p1max); res.p1max.assign(p1, p1 + n);
+                    const double* p2 = (const double*)(b + h->off_p2max); res.p2max.assign(p2, p2 + n);
+                    const int32_t* ps = (const int32_t*)(b + h->off_pos2); res.pos2.assign(ps, ps + n);
+                    res.soft.assign(b + h->off_soft, b + h->off_soft + h->cand_len);
+                    res.hard.assign(b + h->off_hard, b + h->off_hard + h->cand_len);
+                    const int32_t* cv = (const int32_t*)(b + h->off_cov); res.cov.assign(cv, cv + h->cand_len);
+                    if (h->off_counts >= 0) { const double* c = (const double*)(b + h->off_counts); res.counts.assign(c, c + (size_t)5 * h->cand_len); }
+                }
+                r->results->push_back(std::move(res));
+            }
+            r->done = true;
+        }
+        cv_.notify_all();
+    }
+    fb_ctx* ctx_;
+    std::mutex mu_; std::condition_variable cv_;
+    std::vector<Req*> reqs_;
+    int running_;
+    bool failed_ = false; std::string err_;
+    int64_t ticks_ = 0;
+};
+
+static bool parseArgs(int argc, const char* const* argv, Args& a) {
+    if (argc < 16) return false;
+    a.draft = argv[1]; a.maxDistance = atoi(argv[2]); a.readLength = atoi(argv[3]); a.scriptItr = atoi(argv[4]);
+    a.partialFlag = atoi(argv[5]); a.unmapped = atoi(argv[6]); a.numThreads = atoi(argv[7]); a.myout = argv[8];
+    a.tmpDir = argv[9]; a.gapsDir = argv[10]; a.negOverlap = atoi(argv[11]); a.partialReadLen = atoi(argv[12]);
+    a.trim = atoi(argv[13]); a.setInputMean = atoi(argv[14]); a.insertSizeMean = atoi(argv[15]);
+    return true;
+}
+
+template <class F>
+static void parallelFor(int n, int threads, F f) {
+    threads = std::max(1, std::min(threads, n));
+    std::atomic<int> next(0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; t++) th.emplace_back([&] { for (int i; (i = next++) < n;) f(i); });
+    for (auto& t : th) t.join();
+}
+
+static std::vector<int> visibleDevices() {
+    std::vector<int> d;
+    const char* e = getenv("FIGBIRD_GPUS");
+    if (e && *e) { for (const char* p = e; *p;) { d.push_back(atoi(p)); while (*p && *p != ',') p++; if (*p) p++; } }
+    if (d.empty()) d.push_back(0);
+    return d;
+}
+
+struct RunStats { double tLoad = 0, tModel = 0, tPrep = 0, tFill = 0, tWrite = 0; int64_t refPlacements = 0; FbCounters dev{}; int64_t ticks = 0; };
+
+int fillgapsMain(int argc, const char* const* argv) {
+    using clk = std::chrono::steady_clock;
+    auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    Args a;
+    if (!parseArgs(argc, argv, a)) { fprintf(stderr, "usage: fillgaps <15 FillGaps arguments> (FillGaps.cpp:419-433)\n"); return 1; }
+    RunStats rs;
+    auto t0 = clk::now();
+    std::vector<GapRecord> gaps; int totGaps = 0;
+    if (!loadGapRecords(a.tmpDir, gaps, totGaps)) { fprintf(stderr, "Couldn't open gapinfo in Fillgaps.cpp\n"); return 1; }
+    printf("Total # of gaps = %d\n", totGaps);
+    Scaffolds sc;
+    if (!loadScaffolds(a.draft, sc)) { printf("Can't open contig file\n"); return 1; }
+    auto t1 = clk::now();
+    Model model; std::string err;
+    if (!learnModel(a, sc, model, err)) { printf("%s\n", err.c_str()); return 1; }
+    auto t2 = clk::now();
+    if (getenv("FIGBIRD_DUMP_MODEL")) {
+        FILE* fm = fopen(getenv("FIGBIRD_DUMP_MODEL"), "w");
+        if (fm) {
+            fprintf(fm, "mean %.17g leftSD %.17g rightSD %.17g tmin %d tmax %d cutoff %d maxins %d maxread %d\n", model.insertSizeMean, model.leftSD, model.rightSD,
+                    model.insertThresholdMin, model.insertThresholdMax, model.gapProbCutOff, model.maxInsertSize, model.maxReadLength);
+            for (int i = 0; i < model.maxReadLength; i++) fprintf(fm, "pos %d %.17g %.17g %.17g\n", i, model.errorPosDist[i], model.inPosDist[i], model.delPosDist[i]);
+            for (int i = 0; i < 5; i++) fprintf(fm, "etp %d %.17g %.17g %.17g %.17g %.17g\n", i, model.errorTypeProbs[i][0], model.errorTypeProbs[i][1], model.errorTypeProbs[i][2], model.errorTypeProbs[i][3], model.errorTypeProbs[i][4]);
+            for (int i = 0; i < model.maxInsertSize; i++) if (i < 1200 || i % 97 == 0) fprintf(fm, "pdf %d %.17g\n", i, model.insertPdfSmoothed[i]);
+            fclose(fm);
+        }
+    }
+
+    // ---- per-gap inputs + host-only analysis
+    const int nG = (int)gaps.size();
+    std::vector<std::unique_ptr<GapFill>> fills(nG);
+    const int ioThreads = std::max(1, std::min(a.numThreads > 0 ? a.numThreads : 1, 64));
+    parallelFor(nG, std::max(ioThreads, (int)std::thread::hardware_concurrency()), [&](int g) {
+        GapInput in; in.rec = gaps[g];
+        loadPartial(a.gapsDir + "partial_gaps_" + std::to_string(g) + ".sam", in.partial, in.partialExists);
+        if (a.unmapped == 1) loadUnmapped(a.gapsDir + "gaps_" + std::to_string(g) + ".sam", a.readLength, in.unm, in.unmPairCount);
+        fills[g].reset(new GapFill(a, model, sc, std::move(in)));
+        fills[g]->prepare();
+    });
+    auto t3 = clk::now();
+
+    // ---- shard gaps over GPUs: longest-processing-time-first on the cost estimate
+    std::vector<int> devs = visibleDevices();
+    const int nD = (int)devs.size();
+    std::vector<std::vector<int>> shard(nD);
+    {
+        std::vector<int> order(nG); for (int i = 0; i < nG; i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return fills[x]->prepared().cost > fills[y]->prepared().cost; });
+        std::vector<double> load(nD, 0);
+        for (int g : order) { int d = (int)(std::min_element(load.begin(), load.end()) - load.begin()); shard[d].push_back(g); load[d] += fills[g]->prepared().cost + 1; }
+    }
+    std::vector<GapResult> results(nG);
+    std::vector<std::string> devErr(nD);
+    std::vector<FbCounters> devCtr(nD); std::vector<int64_t> devTicks(nD, 0);
+    std::vector<std::thread> devThreads;
+    for (int d = 0; d < nD; d++) devThreads.emplace_back([&, d] {
+        const std::vector<int>& mine = shard[d];
+        if (mine.empty()) return;
+        fb_ctx* ctx = nullptr;
+        if (fb_ctx_create(devs[d], &ctx) != FB_OK || !ctx) { devErr[d] = std::string("fb_ctx_create failed on device ") + std::to_string(devs[d]) + ": " + (ctx ? fb_last_error(ctx) : "no context"); if (ctx) fb_ctx_destroy(ctx); return; }
+        FbModel fm{};
+        fm.max_read_len = model.maxReadLength; fm.err_pos = model.errorPosDist.data(); fm.ins_pos = model.inPosDist.data(); fm.del_pos = model.delPosDist.data();
+        for (int i = 0; i < 5; i++) for (int j = 0; j < 5; j++) fm.err_type[i * 5 + j] = model.errorTypeProbs[i][j];
+        fm.n_insert = model.maxInsertSize; fm.insert_pdf = model.insertPdfSmoothed.data();
+        fm.insert_min = model.insertThresholdMin; fm.insert_max = model.insertThresholdMax; fm.prob_cutoff = model.gapProbCutOff;
+        if (fb_model_upload(ctx, &fm) != FB_OK) { devErr[d] = std::string("fb_model_upload: ") + fb_last_error(ctx); fb_ctx_destroy(ctx); return; }
+        // batch of this shard
+        std::vector<FbGap> fg; std::vector<int32_t> rlen, rmate, pileL, pileR; std::vector<int64_t> roff; std::vector<uint8_t> rfl, rjlo, rjcut, codes, flank;
+        for (int g : mine) {
+            const PreparedGap& p = fills[g]->prepared();
+            FbGap G{}; G.gap_start = p.gapStart; G.mode = p.mode; G.orig_len = p.origLen; G.n_reads = p.supported ? (int)p.readLen.size() : 0;
+            G.read_begin = (int)rlen.size(); G.flank_len = p.flankLen; G.flank_begin = (int)flank.size(); G.pile_len = p.pileLen; G.pile_begin = (int)(pileL.size() / 4);
+            if (p.supported) {
+                for (size_t q = 0; q < p.readLen.size(); q++) {
+                    rlen.push_back(p.readLen[q]); rmate.push_back(p.readMate[q]); rfl.push_back(p.readFlags[q]); rjlo.push_back(p.readJlo[q]); rjcut.push_back(p.readJcut[q]);
+                    roff.push_back((int64_t)codes.size()); codes.insert(codes.end(), p.readCodes[q].begin(), p.readCodes[q].end());
+                }
+                flank.insert(flank.end(), p.flank.begin(), p.flank.end());
+                pileL.insert(pileL.end(), p.pileL.begin(), p.pileL.end()); pileR.insert(pileR.end(), p.pileR.begin(), p.pileR.end());
+            } else { G.flank_len = 0; G.pile_len = 0; }
+            fg.push_back(G);
+        }
+        // keep arrays non-null for empty shards
+        if (rlen.empty()) { rlen.push_back(0); rmate.push_back(0); rfl.push_back(0); rjlo.push_back(0); rjcut.push_back(0); roff.push_back(0); }
+        if (codes.empty()) codes.push_back(4);
+        if (flank.empty()) flank.push_back(4);
+        if (pileL.empty()) { pileL.assign(4, 0); pileR.assign(4, 0); }
+        FbGapBatch B{};
+        B.n_gaps = (int)fg.size(); B.gaps = fg.data(); B.n_reads = (int)rlen.size(); B.read_len = rlen.data(); B.read_code_off = roff.data(); B.read_mate = rmate.data();
+        B.read_flags = rfl.data(); B.read_jlo = rjlo.data(); B.read_jcut = rjcut.data(); B.n_codes = (int64_t)codes.size(); B.read_codes = codes.data();
+        B.n_flank = (int64_t)flank.size(); B.flank_codes = flank.data(); B.n_pile_rows = (int64_t)(pileL.size() / 4); B.pile_left = pileL.data(); B.pile_right = pileR.data();
+        if (fb_batch_upload(ctx, &B) != FB_OK) { devErr[d] = std::string("fb_batch_upload: ") + fb_last_error(ctx); fb_ctx_destroy(ctx); return; }
+
+        int inflight = 512;
+        if (const char* e = getenv("FIGBIRD_INFLIGHT")) inflight = std::max(1, atoi(e));
+        const int workers = std::max(1, std::min((int)mine.size(), inflight));
+        BatchQueue q(ctx, workers);
+        std::atomic<int> next(0);
+        std::vector<std::thread> th;
+        std::mutex emu;
+        for (int w = 0; w < workers; w++) th.emplace_back([&] {
+            try {
+                for (int i; (i = next++) < (int)mine.size();) { int g = mine[i]; results[g] = fills[g]->run(q, i); }
+            } catch (const std::exception& e) { std::lock_guard<std::mutex> l(emu); devErr[d] = e.what(); }
+            q.workerExit();
+        });
+        for (auto& t : th) t.join();
+        fb_get_counters(ctx, &devCtr[d]); devTicks[d] = q.ticks();
+        fb_ctx_destroy(ctx);
+    });
+    for (auto& t : devThreads) t.join();
+    for (auto& e : devErr) if (!e.empty()) { fprintf(stderr, "figbird_b200: %s\n", e.c_str()); return 1; }
+    auto t4 = clk::now();
+
+    // ---- outputs (gaps beyond the shorter of gapInfo/stat2 keep an empty entry, like a missing worker line)
+    if (!writeGapout(a.tmpDir + "gapout.txt", gaps, results)) { fprintf(stderr, "cannot write gapout.txt\n"); return 1; }
+    {
+        FILE* df = fopen((a.tmpDir + "draw.txt").c_str(), "w");
+        if (df) { for (auto& r : results) fputs(r.drawText.c_str(), df); fclose(df); }
+    }
+    if (!writeFilledContigs(a.tmpDir, sc, gaps, results, totGaps)) { fprintf(stderr, "cannot write filledContigs.fa\n"); return 1; }
+    auto t5 = clk::now();
+    rs.tLoad = secs(t0, t1); rs.tModel = secs(t1, t2); rs.tPrep = secs(t2, t3); rs.tFill = secs(t3, t4); rs.tWrite = secs(t4, t5);
+    for (auto& r : results) rs.refPlacements += r.refPlacements;
+    for (int d = 0; d < nD; d++) {
+        rs.dev.placements_p1 += devCtr[d].placements_p1; rs.dev.placements_p2 += devCtr[d].placements_p2; rs.dev.base_terms += devCtr[d].base_terms;
+        rs.dev.kernel_launches += devCtr[d].kernel_launches; rs.dev.device_ms = std::max(rs.dev.device_ms, devCtr[d].device_ms);
+        rs.dev.h2d_bytes += devCtr[d].h2d_bytes; rs.dev.d2h_bytes += devCtr[d].d2h_bytes; rs.ticks += devTicks[d];
+    }
+    if (const char* mp = getenv("FIGBIRD_METRICS")) {
+        FILE* mf = fopen(mp, "w");
+        if (mf) {
+            fprintf(mf, "{\"engine\": \"%s\", \"gaps\": %d, \"gpus\": %d, \"t_load\": %.6f, \"t_model\": %.6f, \"t_prepare\": %.6f, \"t_fill\": %.6f, \"t_write\": %.6f, "
+                        "\"ref_placements_p1\": %lld, \"dev_placements_p1\": %lld, \"dev_placements_p2\": %lld, \"dev_base_terms\": %lld, \"kernel_launches\": %lld, "
+                        "\"device_ms\": %.6f, \"h2d_bytes\": %lld, \"d2h_bytes\": %lld, \"ticks\": %lld}\n",
+                    fb_engine_name(), nG, nD, rs.tLoad, rs.tModel, rs.tPrep, rs.tFill, rs.tWrite, (long long)rs.refPlacements, (long long)rs.dev.placements_p1,
+                    (long long)rs.dev.placements_p2, (long long)rs.dev.base_terms, (long long)rs.dev.kernel_launches, rs.dev.device_ms, (long long)rs.dev.h2d_bytes,
+                    (long long)rs.dev.d2h_bytes, (long long)rs.ticks);
+            fclose(mf);
+        }
+    }
+    printf("Time taken = %d seconds\n", (int)secs(t0, t5));
+    printf("======================================\nIteration %d ends successfully\n======================================\n", a.scriptItr);
+    return 0;
+}
+
+}  // namespace fb
+
+extern "C" int32_t fb_fillgaps_main(int32_t argc, const char* const* argv) {
+    try { return fb::fillgapsMain(argc, argv); }
+    catch (const std::exception& e) { fprintf(stderr, "figbird_b200: %s\n", e.what()); return 1; }
+}

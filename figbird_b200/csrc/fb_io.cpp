@@ -1,0 +1,212 @@
+// fb_io.cpp -- file formats on the gap-fill path: scaffold FASTA, gapInfo/stat2,
+// per-gap read files in; gapout.txt / filledContigs.fa / Ncount.txt / draw.txt out.
+#include <cctype>
+#include <cstdlib>
+#include <cstring>
+
+#include "fb_host.h"
+#include "fb_io.h"
+
+namespace fb {
+
+// The reference reads the FASTA with fgets into a 1024-byte buffer (Figbird.cpp:6986-7046, same code in
+// FillGaps.cpp:716-771): a chunk shorter than 1023 chars loses its last char (the newline); a chunk of
+// exactly 1023 chars is kept whole -- even when its last char is the newline.  Scaffold lengths and hence
+// every coordinate depend on that, so the loader works on the same 1023-char chunks.
+bool loadScaffolds(const std::string& path, Scaffolds& out) {
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) return false;
+    std::string text;
+    { char buf[1 << 16]; size_t n; while ((n = fread(buf, 1, sizeof buf, f)) > 0) text.append(buf, n); }
+    fclose(f);
+    const size_t CH = 1023;
+    std::string cur;
+    size_t p = 0;
+    while (p < text.size()) {
+        size_t e = text.find('\n', p);
+        size_t lineEnd = e == std::string::npos ? text.size() : e + 1;   // physical line incl. '\n'
+        for (size_t c = p; c < lineEnd; c += CH) {
+            size_t n = std::min(CH, lineEnd - c);
+            const char* chunk = text.data() + c;
+            if (chunk[0] == ';') continue;
+            if (chunk[0] == '>') {
+                std::string nm(chunk + 1, n >= 2 ? n - 2 : 0);          // drop '>' and the last char
+                size_t a = nm.find_first_not_of(" \t\n"), b = a == std::string::npos ? a : nm.find_first_of(" \t\n", a);
+                out.names.push_back(a == std::string::npos ? std::string() : nm.substr(a, b == std::string::npos ? b : b - a));
+                if (!cur.empty()) { out.seq.push_back(cur); cur.clear(); }
+            } else {
+                if (n < CH) cur.append(chunk, n - 1); else cur.append(chunk, n);
+            }
+        }
+        p = lineEnd;
+    }
+    out.seq.push_back(cur);
+    out.totalLength = 0;
+    for (auto& s : out.seq) { for (auto& ch : s) ch = (char)toupper((unsigned char)ch); out.totalLength += (long)s.size(); }
+    return true;
+}
+
+static bool readLines(const std::string& path, std::vector<std::string>& lines) {
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) return false;
+    char buf[1024];   // MAX_REC_LEN: a longer physical line arrives as several fgets chunks, like the reference sees it
+    while (fgets(buf, sizeof buf, f)) lines.emplace_back(buf);
+    fclose(f);
+    return true;
+}
+
+bool loadGapRecords(const std::string& tmpDir, std::vector<GapRecord>& gaps, int& totGaps) {
+    std::vector<std::string> gi, s2;
+    if (!readLines(tmpDir + "gapInfo.txt", gi)) return false;
+    readLines(tmpDir + "stat2.txt", s2);
+    totGaps = (int)gi.size();
+    size_t n = std::min(gi.size(), s2.size());   // Figbird.cpp:7329 stops at the shorter file
+    for (size_t i = 0; i < n; i++) {
+        GapRecord r; r.gapNo = (int)i;
+        long a = 0, b = 0, c = 0;
+        sscanf(gi[i].c_str(), "%ld\t%ld\t%ld", &a, &b, &c);
+        r.contigNo = (int)a; r.gapStart = b; r.gapLength = (int)c;
+        int x = 0, y = 0, z = 0;
+        sscanf(s2[i].c_str(), "%d\t%d\t%d", &x, &y, &z);
+        r.stat1 = x; r.stat2 = y; r.stat3 = z;
+        gaps.push_back(r);
+    }
+    return true;
+}
+
+static std::vector<std::string> splitTabs(const std::string& line) {
+    // strtok(line, "\t") semantics: runs of tabs collapse, the newline stays in the last token
+    std::vector<std::string> t;
+    size_t p = 0;
+    while (p < line.size()) {
+        while (p < line.size() && line[p] == '\t') p++;
+        if (p >= line.size()) break;
+        size_t e = line.find('\t', p);
+        if (e == std::string::npos) e = line.size();
+        t.push_back(line.substr(p, e - p));
+        p = e;
+    }
+    return t;
+}
+
+// partial_gaps_<g>.sam: seq, clipped_index, match, pos, cigar, pos2, qual (Preprocess.cpp:454,466,478).
+// Every reader in the reference stops after partial_limit+1 = 3001 lines (e.g. Figbird.cpp:1814,2014).
+bool loadPartial(const std::string& path, std::vector<PartialRead>& out, bool& exists) {
+    std::vector<std::string> lines;
+    exists = readLines(path, lines);
+    if (!exists) return false;
+    for (auto& ln : lines) {
+        auto t = splitTabs(ln);
+        PartialRead r;
+        if (t.size() >= 1) r.seq = t[0];
+        if (t.size() >= 2) r.clippedIndex = atoi(t[1].c_str());
+        if (t.size() >= 3) r.match = atoi(t[2].c_str());
+        if (t.size() >= 4) r.pos = atoi(t[3].c_str());
+        if (t.size() >= 6) r.refPos = atoi(t[5].c_str());
+        if (t.size() >= 7) { r.qual = t[6]; while (!r.qual.empty() && (r.qual.back() == '\n' || r.qual.back() == '\r')) r.qual.pop_back(); }
+        if (t.size() == 1) { while (!r.seq.empty() && r.seq.back() == '\n') r.seq.pop_back(); }
+        out.push_back(r);
+        if (out.size() > 3000) break;
+    }
+    return true;
+}
+
+static char rc(char ch) {   // reverse(), Figbird.cpp:1427-1449
+    switch (ch) { case 'A': case 'a': return 'T'; case 'C': case 'c': return 'G'; case 'G': case 'g': return 'C'; case 'T': case 't': return 'A'; }
+    return 'N';
+}
+
+// gaps_<g>.sam (parseUnmapped, Figbird.cpp:5661-5767): line pairs, mapped mate then unmapped mate.
+// pairCount = findcount_file(.,0) (Figbird.cpp:6686-6711).
+bool loadUnmapped(const std::string& path, int readLen, std::vector<UnmappedRead>& out, int& pairCount) {
+    std::vector<std::string> lines;
+    pairCount = 0;
+    if (!readLines(path, lines)) return false;
+    { size_t i = 0; while (i < lines.size()) { i++; if (i >= lines.size()) break; i++; pairCount++; } }
+    size_t i = 0; int total = 0;
+    while (i < lines.size()) {
+        const std::string& l1 = lines[i++];
+        if (l1[0] == '@') continue;
+        if (l1.size() < 60) continue;
+        if (i >= lines.size()) break;
+        const std::string& l2 = lines[i++];
+        auto t1 = splitTabs(l1), t2 = splitTabs(l2);
+        if (t1.size() < 4 || t2.size() < 8) continue;
+        UnmappedRead r;
+        int flag = atoi(t1[1].c_str());
+        int strand1 = (flag & 16) >> 4;
+        r.matePos = atoi(t1[3].c_str());
+        r.seq = t2[6];
+        (void)readLen;
+        if (strand1 == 0) {
+            std::string rev(r.seq.size(), 'N');
+            for (size_t k = 0; k < r.seq.size(); k++) rev[r.seq.size() - 1 - k] = rc(r.seq[k]);
+            r.seq = rev; r.isReverse = 1;
+        } else r.isReverse = 0;
+        out.push_back(r);
+        if (++total == 3000) break;   // unmapped_limit
+    }
+    return true;
+}
+
+// ---- writers -------------------------------------------------------------------------------------------
+
+bool writeGapout(const std::string& path, const std::vector<GapRecord>& gaps, const std::vector<GapResult>& res) {
+    FILE* f = fopen(path.c_str(), "w");
+    if (!f) return false;
+    for (size_t i = 0; i < gaps.size(); i++) {
+        // Figbird.cpp:7413 then re-emitted by FillGaps.cpp:204-207 (an empty string leaves a bare tab)
+        fprintf(f, "%d\t%d\t%ld\t%d\t%d\t", gaps[i].gapNo, gaps[i].contigNo, gaps[i].gapStart, gaps[i].gapLength, res[i].gapStringLength);
+        if (res[i].gapStringLength > 0) fprintf(f, "%s\n", res[i].gapString.c_str()); else fprintf(f, "\n");
+    }
+    fclose(f);
+    return true;
+}
+
+// FillGaps.cpp:820-926: splice the gap strings into the scaffolds, trim after negative-overlap gaps,
+// and report whether any N is left (with the stale-string quirk of :861-870).
+bool writeFilledContigs(const std::string& tmpDir, const Scaffolds& sc, const std::vector<GapRecord>& gaps,
+                        const std::vector<GapResult>& res, int totGaps) {
+    FILE* out = fopen((tmpDir + "filledContigs.fa").c_str(), "w");
+    FILE* nf = fopen((tmpDir + "Ncount.txt").c_str(), "w");
+    if (!out || !nf) { if (out) fclose(out); if (nf) fclose(nf); return false; }
+    std::vector<int> gtf(std::max(totGaps, (int)gaps.size()) + 1, 0);
+    for (size_t i = 0; i < res.size(); i++) gtf[i] = res[i].gapToFill;
+    int gapCount = -1; size_t nextEntry = 0;
+    int nStart = 0;
+    long newNcount = 0;
+    std::string gapString;          // persists between gaps like the reference's stack buffer
+    int gapStringLength = 0;
+    std::string buf;
+    for (size_t i = 0; i < sc.seq.size(); i++) {
+        const std::string& s = sc.seq[i];
+        fprintf(out, ">%s\n", i < sc.names.size() ? sc.names[i].c_str() : "");
+        buf.clear();
+        for (size_t j = 0; j < s.size(); j++) {
+            bool isN = (s[j] == 'N' || s[j] == 'n');
+            if (isN && nStart == 0) { nStart = 1; gapCount++; }
+            if (!isN || j == s.size() - 1) {
+                if (nStart == 1) {
+                    if (nextEntry < res.size()) {
+                        gapStringLength = res[nextEntry].gapStringLength;
+                        if (gapStringLength > 0) gapString = res[nextEntry].gapString;
+                        nextEntry++;
+                    }
+                    for (char ch : gapString) if (ch == 'N') newNcount++;
+                    fputs(buf.c_str(), out);
+                    if (gapStringLength > 0) fputs(gapString.c_str(), out);
+                    buf.clear();
+                    nStart = 0;
+                }
+                if (gapCount >= 0 && gapCount < (int)gtf.size() && gtf[gapCount] > 0) gtf[gapCount]--;
+                else buf.push_back(s[j]);
+            }
+        }
+        fprintf(out, "%s\n", buf.c_str());
+    }
+    fprintf(nf, "%d", newNcount == 0 ? 0 : 1);
+    fclose(out); fclose(nf);
+    return true;
+}
+
+}  // namespace fb

@@ -1,0 +1,350 @@
+// fb_model.cpp -- the learned insert-size / error-model tables.
+//
+// Host-side, once per run (the reference repeats this in every worker process).  The tables must be
+// numerically identical to the reference's because every threshold downstream is applied to them, so the
+// arithmetic below keeps the reference's types and evaluation order:
+//   sufficient statistics   Figbird.cpp:846-921 (processMapping), :186-225 (updateInsertCounts),
+//                           :291-487 (processErrorTypes), :255-275 (getLength)
+//   normalisation           Figbird.cpp:497-844 (computeProbabilites)
+//   cut-off / thresholds    Figbird.cpp:952-1376 (computeErrorProb, computeLikelihood), :7155-7200
+// including its quirks (the MD string is compared with the CIGAR of an error-free read, so every read takes
+// the error path, :297; soft clips count as insertions, :339; computeErrorProb does not split CIGARs at 'S', :988).
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+
+#include "fb_host.h"
+
+namespace fb {
+namespace {
+
+// strtok(3) semantics on a private buffer (the reference tokenises every SAM line with strtok).
+struct Tokens {
+    char* p;
+    explicit Tokens(char* s) : p(s) {}
+    char* next(const char* delim) {
+        if (!p) return nullptr;
+        p += strspn(p, delim);
+        if (!*p) { p = nullptr; return nullptr; }
+        char* tok = p;
+        p += strcspn(p, delim);
+        if (*p) { *p = '\0'; p++; } else p = nullptr;
+        return tok;
+    }
+};
+
+inline int baseIndex(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 4; }
+
+struct Stats {
+    int maxReadLength, MAX_INSERT_SIZE, maxInsertSize;
+    std::vector<long> insertCounts;
+    long errorTypes[5][5]; long baseCounts[5];
+    std::vector<long> errorPos, inPos, inLengths, delPos, delLengths, readLengths;
+    long discardedReads = 0, uniqueMappedReads = 0;
+};
+
+void bumpInsert(Stats& s, int index) {   // Figbird.cpp:186-225
+    if (index <= 0) return;
+    if (index < s.maxInsertSize) { s.insertCounts[index]++; return; }
+    if (index > s.MAX_INSERT_SIZE) { s.discardedReads++; return; }
+    int grown = std::max(s.maxInsertSize * 2, index);
+    s.insertCounts.resize(grown, 1);
+    s.insertCounts[index]++;
+    s.maxInsertSize = grown;
+}
+
+// One CIGAR walk shared by the two passes.  `delims` is what strtok splits on (the two reference
+// functions differ: "IDMS^\t\n " vs "IDM^\t\n ").  The op letter is looked up in the ORIGINAL string at the
+// running offset, exactly as the reference does (Figbird.cpp:325-375, 988-1039).
+template <class OnOp>
+void walkCigar(const char* cigar, const char* delims, OnOp onOp) {
+    char buf[1024];
+    strncpy(buf, cigar, sizeof buf - 1); buf[sizeof buf - 1] = 0;
+    Tokens tk(buf);
+    int consumed = 0;
+    const size_t clen = strlen(cigar);
+    for (char* t = tk.next(delims); t; t = tk.next(delims)) {
+        int n = atoi(t);
+        consumed += (int)strlen(t);
+        char op = (size_t)consumed <= clen ? cigar[consumed] : '\0';
+        onOp(op, n);
+        consumed++;
+    }
+}
+
+// The MD walk (Figbird.cpp:378-484, 1042-1149): calls onMismatch(from, readIndexBase) for each substitution.
+template <class OnMis>
+void walkMD(const char* md, const std::vector<int>& inserts, OnMis onMis) {
+    char buf[1024];
+    strncpy(buf, md, sizeof buf - 1); buf[sizeof buf - 1] = 0;
+    const unsigned long mdLength = strlen(md) - 5;
+    Tokens tk(buf);
+    tk.next(":"); tk.next(":");
+    int index = 0; unsigned long totalLength = 0;
+    for (char* t = tk.next("ACGTN^\t\n "); t; t = tk.next("ACGTN^\t\n ")) {
+        totalLength += strlen(t);
+        if (totalLength < mdLength) {
+            char from = md[5 + totalLength];
+            if (from == '^') {
+                totalLength++;
+                index += atoi(t);
+                for (unsigned long i = totalLength; i < mdLength; i++) {
+                    from = md[5 + totalLength];
+                    if (from == 'A' || from == 'C' || from == 'G' || from == 'T' || from == 'N') totalLength++;
+                    else break;
+                }
+            } else if (from == 'A' || from == 'C' || from == 'G' || from == 'T' || from == 'N') {
+                totalLength++;
+                index += atoi(t) + 1;
+                int curIndex = 0;
+                for (int i = 0; i < index && i < (int)inserts.size(); i++) curIndex += inserts[i];
+                onMis(from, index, curIndex);
+            } else break;
+        }
+    }
+}
+
+struct SamFields { char* qname; int flag; char* rname; int pos; char* cigar; int tlen; char* seq; char md[1000]; int nh; bool haveMd, haveNh; };
+
+// Figbird.cpp:864-901: columns of a myout.sam line (the file has 10 columns, Preprocess.cpp:412-416)
+bool splitMyout(char* line, SamFields& f, char* mdKeep /*persisting MD buffer*/) {
+    Tokens tk(line);
+    f.qname = tk.next("\t"); char* t = tk.next("\t"); if (!f.qname || !t) return false;
+    f.flag = atoi(t);
+    f.rname = tk.next("\t"); t = tk.next("\t"); if (!f.rname || !t) return false;
+    f.pos = atoi(t);
+    f.cigar = tk.next("\t"); t = tk.next("\t"); f.seq = tk.next("\t");
+    if (!f.cigar || !t || !f.seq) return false;
+    f.tlen = atoi(t);
+    f.haveMd = f.haveNh = false;
+    while ((t = tk.next("\t\n")) != nullptr) {
+        if (t[0] == 'M' && t[1] == 'D') { strncpy(mdKeep, t, 999); mdKeep[999] = 0; f.haveMd = true; }
+        else if (t[0] == 'I' && t[1] == 'H') { f.nh = atoi(t + 5); f.haveNh = true; }
+    }
+    return true;
+}
+
+}  // namespace
+
+bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err) {
+    // ---- stat.txt (Figbird.cpp:7084-7093)
+    int maxIns = 0;
+    {
+        FILE* f = fopen((a.tmpDir + "stat.txt").c_str(), "r");
+        if (!f) { err = "Can't open " + a.tmpDir + "stat.txt"; return false; }
+        if (fscanf(f, "%ld %ld %d %d", &m.totalCount, &m.unCount, &m.maxReadLength, &maxIns) != 4) { fclose(f); err = "bad stat.txt"; return false; }
+        fclose(f);
+    }
+    Stats s;
+    s.maxReadLength = m.maxReadLength;
+    s.MAX_INSERT_SIZE = maxIns > 20000 ? maxIns : 20000;
+    s.maxInsertSize = s.MAX_INSERT_SIZE;
+    s.insertCounts.assign(s.maxInsertSize, 1);
+    for (auto& r : s.errorTypes) for (auto& v : r) v = 1;
+    for (auto& v : s.baseCounts) v = 1;
+    const int RL = m.maxReadLength;
+    s.errorPos.assign(RL, 1); s.inPos.assign(RL, 1); s.inLengths.assign(RL, 1); s.delPos.assign(RL, 1); s.delLengths.assign(RL, 1); s.readLengths.assign(RL, 0);
+    const double inputMean = a.setInputMean == 1 ? (double)a.insertSizeMean : 0.0;   // Figbird.cpp:6973
+
+    FILE* mf = fopen(a.myout.c_str(), "r");
+    if (!mf) { err = "Can't open map file"; return false; }
+    // whole file in memory once; both passes walk the same lines (the reference reads it twice per worker)
+    std::vector<char> text;
+    { fseek(mf, 0, SEEK_END); long n = ftell(mf); fseek(mf, 0, SEEK_SET); text.resize(n + 1); size_t got = fread(text.data(), 1, n, mf); text[got] = 0; text.resize(got + 1); fclose(mf); }
+    std::vector<char*> lines;
+    for (char* p = text.data(); *p;) { lines.push_back(p); char* e = strchr(p, '\n'); if (!e) break; p = e + 1; }
+    // NB: lines keep their '\n'; tokenisers treat it as a delimiter where the reference does.
+
+    std::vector<char> scratch(2048);
+    char mdKeep[1000]; mdKeep[0] = 0;
+    // ---- pass 1: processMapping
+    for (char* ln : lines) {
+        if (ln[0] == '@') continue;
+        size_t len = strcspn(ln, "\n"); if (len > 1022) len = 1022;   // fgets(1024)
+        scratch.assign(ln, ln + len + 1); scratch[len] = '\n'; scratch.push_back(0);
+        SamFields f;
+        if (!splitMyout(scratch.data(), f, mdKeep)) continue;
+        if (!(f.nh == 1 && mdKeep[5] != '^')) continue;
+        long contigNo = atol(f.rname);
+        if (contigNo >= 0 && contigNo < (long)sc.seq.size() && (double)sc.seq[contigNo].size() > inputMean) bumpInsert(s, f.tlen);
+        // processErrorTypes
+        const int strand = (f.flag & 16) >> 4;
+        int readLength = 0;
+        for (const char* c = f.seq; *c; c++, readLength++) s.baseCounts[baseIndex(*c)]++;
+        if (readLength < 1 || readLength > RL) continue;
+        s.readLengths[readLength - 1]++;
+        std::vector<int> inserts(readLength, 0);
+        int index = 0, curIndex = 0;
+        walkCigar(f.cigar, "IDMS^\t\n ", [&](char op, int n) {
+            if (op == 'M') { index += n; curIndex += n; }
+            else if (op == 'I' || op == 'S') {
+                int at = strand == 0 ? index : readLength - index - 1;
+                if (at >= 0 && at < RL) s.inPos[at]++;
+                if (n >= 1 && n <= RL) s.inLengths[n - 1]++;
+                if (curIndex >= 0 && curIndex < readLength) inserts[curIndex] = n;
+                index += n;
+            } else if (op == 'D') {
+                int at = strand == 0 ? index : readLength - index - 1;
+                if (at >= 0 && at < RL) s.delPos[at]++;
+                if (n >= 1 && n <= RL) s.delLengths[n - 1]++;
+            }
+        });
+        walkMD(mdKeep, inserts, [&](char from, int idx, int cur) {
+            int ri = idx - 1 + cur;
+            char to = (ri >= 0 && ri < readLength) ? f.seq[ri] : 'N';
+            int at = strand == 0 ? ri : readLength - idx - cur;
+            if (at >= 0 && at < RL) s.errorPos[at]++;
+            int fi = baseIndex(from), ti = baseIndex(to);
+            if (fi != ti) s.errorTypes[fi][ti]++;
+        });
+        s.uniqueMappedReads++;
+    }
+
+    // ---- computeProbabilites (Figbird.cpp:497-844); only the quantities used downstream are kept
+    double baseErrorRates[5];
+    for (int i = 0; i < 5; i++) {
+        int errorCount = 0;
+        for (int j = 0; j < 5; j++) errorCount += s.errorTypes[i][j];
+        for (int j = 0; j < 5; j++) m.errorTypeProbs[i][j] = (double)s.errorTypes[i][j] / errorCount;
+        baseErrorRates[i] = errorCount / (double)s.baseCounts[i];
+    }
+    { double sum = 0; for (int i = 0; i < 4; i++) sum += baseErrorRates[i]; for (int i = 0; i < 4; i++) baseErrorRates[i] = 4 * baseErrorRates[i] / sum; baseErrorRates[4] = 1; }
+    for (int i = RL - 1; i > 0; i--) s.readLengths[i - 1] = s.readLengths[i] + s.readLengths[i - 1];
+    m.errorPosDist.resize(RL); m.inPosDist.resize(RL); m.delPosDist.resize(RL);
+    std::vector<double> inLengthDist(RL), delLengthDist(RL);
+    for (int i = 0; i < RL; i++) m.errorPosDist[i] = (double)s.errorPos[i] / s.readLengths[i];
+    for (int i = 0; i < RL; i++) m.inPosDist[i] = (double)s.inPos[i] / s.readLengths[i];
+    { int c = 0; for (int i = 0; i < RL; i++) c += s.inLengths[i]; for (int i = 0; i < RL; i++) inLengthDist[i] = (double)s.inLengths[i] / c; }
+    for (int i = 0; i < RL; i++) m.delPosDist[i] = (double)s.delPos[i] / s.readLengths[i];
+    { int c = 0; for (int i = 0; i < RL; i++) c += s.delLengths[i]; for (int i = 0; i < RL; i++) delLengthDist[i] = (double)s.delLengths[i] / c; }
+
+    const int MI = s.maxInsertSize;
+    m.maxInsertSize = MI;
+    std::vector<double> insertLengthDist(MI);
+    long insCount = s.discardedReads;
+    double sum = 0;
+    for (int i = 0; i < MI; i++) { insCount += (s.insertCounts[i] - 1); sum += i * (s.insertCounts[i] - 1); }
+    m.insertSizeMean = sum / insCount;
+    const double mean = m.insertSizeMean;
+    sum = 0;
+    for (int i = 0; i < MI; i++) { insertLengthDist[i] = (double)s.insertCounts[i] / insCount; sum += (s.insertCounts[i] - 1) * (mean - i) * (mean - i); }
+    std::vector<double> noErrorProbs(RL);
+    { double p = 1.0; for (int i = 0; i < RL; i++) { p *= (1 - m.errorPosDist[i] - m.inPosDist[i] - m.delPosDist[i]); noErrorProbs[i] = p; } }
+
+    const int W = 12;   // windowSize, Figbird.cpp:89
+    m.insertPdfSmoothed.assign(MI, 0.0);
+    {
+        std::vector<double>& sm = m.insertPdfSmoothed;
+        double windowSum = 0;
+        for (int i = 0; i < W; i++) sm[i] = insertLengthDist[i];
+        for (int i = 0; i < 2 * W + 1; i++) windowSum += insertLengthDist[i];
+        sm[W] = windowSum / (2 * W + 1);
+        for (int i = W + 1; i < MI - W; i++) { windowSum -= insertLengthDist[i - W - 1]; windowSum += insertLengthDist[i + W]; sm[i] = windowSum / (2 * W + 1); }
+        for (int i = MI - W; i < MI; i++) sm[i] = insertLengthDist[i];
+        for (int i = 0; i < MI; i++) sm[i] = sm[i] - 1 / (double)(insCount) + (1 / (double)MI) / (double)(insCount + 1);
+    }
+    {   // one-sided SDs about the mean (Figbird.cpp:785-802)
+        double insertSum = 0, insertCount = 0;
+        for (int i = mean + 1; i < MI; i++) { insertSum = insertSum + (s.insertCounts[i] - 1) * (i - mean) * (i - mean); insertCount += (s.insertCounts[i] - 1); }
+        m.rightSD = sqrt(insertSum / insertCount);
+        insertSum = 0; insertCount = 0;
+        for (int i = std::max((int)(mean - 10 * m.rightSD), 0); i < mean; i++) { insertSum = insertSum + (s.insertCounts[i] - 1) * (mean - i) * (mean - i); insertCount += (s.insertCounts[i] - 1); }
+        m.leftSD = sqrt(insertSum / insertCount);
+    }
+    m.uniqueMappedReads = s.uniqueMappedReads;
+
+    // ---- pass 2: computeLikelihood -> gapProbs histogram (Figbird.cpp:1156-1376)
+    long totalContigLength = 0;
+    for (auto& q : sc.seq) totalContigLength += (long)q.size();
+    std::vector<long> effectiveLengths(MI, -1);
+    effectiveLengths[0] = totalContigLength;
+    auto effLen = [&](int insertSize) -> long {
+        if (insertSize < 0) return effectiveLengths[0];
+        auto compute = [&]() { long e = 0; for (auto& q : sc.seq) if ((long)q.size() >= insertSize) e += ((long)q.size() - insertSize + 1); return e; };
+        if (insertSize >= MI) return compute();
+        if (effectiveLengths[insertSize] == -1) effectiveLengths[insertSize] = compute();
+        return effectiveLengths[insertSize];
+    };
+    auto errorProb = [&](const char* cigar, const char* md, const char* read, int strand) -> long double {
+        const unsigned long readLength = strlen(read);
+        long double ep = (readLength >= 1 && (int)readLength <= RL) ? noErrorProbs[readLength - 1] : 0;
+        if (md[5] == '^') return ep;
+        std::vector<int> inserts(readLength, 0);
+        int index = 0, curIndex = 0;
+        walkCigar(cigar, "IDM^\t\n ", [&](char op, int n) {
+            if (op == 'M') { index += n; curIndex += n; }
+            else if (op == 'I') {
+                unsigned long i = strand == 0 ? (unsigned long)index : readLength - index - 1;
+                if (i < (unsigned long)RL && n >= 1 && n <= RL)
+                    ep = ep * m.inPosDist[i] * inLengthDist[n - 1] / (1 - m.errorPosDist[i] - m.inPosDist[i] - m.delPosDist[i]);
+                if (curIndex >= 0 && curIndex < (int)readLength) inserts[curIndex] = n;
+                index += n;
+            } else if (op == 'D') {
+                unsigned long i = strand == 0 ? (unsigned long)index : readLength - index - 1;
+                if (i < (unsigned long)RL && n >= 1 && n <= RL)
+                    ep = ep * m.delPosDist[i] * delLengthDist[n - 1] / (1 - m.errorPosDist[i] - m.inPosDist[i] - m.delPosDist[i]);
+            }
+        });
+        walkMD(md, inserts, [&](char from, int idx, int cur) {
+            int ri = idx - 1 + cur;
+            char to = (ri >= 0 && ri < (int)readLength) ? read[ri] : '\0';
+            int i = strand == 0 ? ri : (int)readLength - idx - cur;
+            if (i >= 0 && i < RL) ep = ep * m.errorPosDist[i] / (1 - m.errorPosDist[i] - m.inPosDist[i] - m.delPosDist[i]);
+            int fi = baseIndex(from), ti = baseIndex(to);
+            if (fi != ti) ep *= baseErrorRates[fi] * m.errorTypeProbs[fi][ti];
+        });
+        return ep;
+    };
+
+    long gapProbs[1000] = {0};
+    {
+        std::string pre1 = "*", pre2 = "*";
+        long double tempProb = 0, gapProb = 0;
+        char md1[1000], md2[1000]; md1[0] = md2[0] = 0;
+        std::vector<char> b1(2048), b2(2048);
+        size_t li = 0;
+        while (li < lines.size()) {
+            char* l1 = lines[li++];
+            if (l1[0] == '@') continue;
+            if (li >= lines.size()) break;
+            char* l2 = lines[li++];
+            size_t n1 = strcspn(l1, "\n"), n2 = strcspn(l2, "\n");
+            if (n1 > 1022) n1 = 1022; if (n2 > 1022) n2 = 1022;
+            b1.assign(l1, l1 + n1 + 1); b1[n1] = '\n'; b1.push_back(0);
+            b2.assign(l2, l2 + n2 + 1); b2[n2] = '\n'; b2.push_back(0);
+            SamFields f1, f2;
+            if (!splitMyout(b1.data(), f1, md1) || !splitMyout(b2.data(), f2, md2)) continue;
+            int insertSize = std::max(f1.tlen, f2.tlen);
+            long double insertSizeProb = 0;
+            if (insertSize >= 0 && insertSize < MI) insertSizeProb = insertLengthDist[insertSize];
+            if (insertSizeProb == 0) insertSizeProb = 1 / (double)s.uniqueMappedReads;
+            long double e1 = errorProb(f1.cigar, md1, f1.seq, (f1.flag & 16) >> 4);
+            long double e2 = errorProb(f2.cigar, md2, f2.seq, (f2.flag & 16) >> 4);
+            long eff = effLen(insertSize);
+            long double prob = (1 / (long double)(eff)) * insertSizeProb * e1 * e2;
+            if (pre1 == f1.qname && pre2 == f2.qname) {
+                if (tempProb < prob) { tempProb = prob; gapProb = e2; }
+            } else if (pre1 != "*" && pre2 != "*") {
+                int gapIndex = -std::log10(gapProb);
+                gapIndex++;
+                if (gapIndex < 1000 && gapIndex >= 0) gapProbs[gapIndex]++; else gapProbs[999]++;
+                tempProb = prob; gapProb = e2;
+            } else { tempProb = prob; gapProb = e2; }
+            pre1 = f1.qname; pre2 = f2.qname;
+        }
+    }
+    {   // Figbird.cpp:7155-7178
+        long gapProbSum = 0; for (int i = 0; i < 1000; i++) gapProbSum += gapProbs[i];
+        long gapProbCount = 0; const double value = .8;
+        m.gapProbCutOff = 0;
+        for (int i = 0; i < 1000; i++) { gapProbCount += gapProbs[i]; if (gapProbCount >= value * gapProbSum) { m.gapProbCutOff = i; break; } }
+    }
+    // ---- insert thresholds (Figbird.cpp:7188-7200)
+    m.insertThresholdMin = std::max((int)(mean - 3 * m.leftSD), 1);
+    m.insertThresholdMax = std::min((int)(mean + 3 * m.rightSD), MI);
+    if (a.partialFlag) { m.insertThresholdMin -= a.partialReadLen; m.insertThresholdMax += a.partialReadLen; }
+    return true;
+}
+
+}  // namespace fb

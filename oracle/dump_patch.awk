@@ -12,5 +12,15 @@
         print "        fflush(fbd);} }";
         done = 1;
     }
+    if ($0 ~ /Done with insertthteshold/ && !mdone) {
+        print "    { const char* fbn=getenv(\"FB_DUMP_MODEL\"); if(fbn){ FILE* fm=fopen(fbn,\"w\");";
+        print "      fprintf(fm,\"mean %.17g leftSD %.17g rightSD %.17g tmin %d tmax %d cutoff %d maxins %d maxread %d\\n\",insertSizeMean,leftSD,rightSD,insertThresholdMin,insertThresholdMax,gapProbCutOff,maxInsertSize,maxReadLength);";
+        print "      for(int fi=0;fi<maxReadLength;fi++)fprintf(fm,\"pos %d %.17g %.17g %.17g\\n\",fi,errorPosDist[fi],inPosDist[fi],delPosDist[fi]);";
+        print "      for(int fi=0;fi<5;fi++)fprintf(fm,\"etp %d %.17g %.17g %.17g %.17g %.17g\\n\",fi,errorTypeProbs[fi][0],errorTypeProbs[fi][1],errorTypeProbs[fi][2],errorTypeProbs[fi][3],errorTypeProbs[fi][4]);";
+        print "      for(int fi=0;fi<maxInsertSize;fi++)if(fi<1200||fi%97==0)fprintf(fm,\"pdf %d %.17g\\n\",fi,insertLengthDistSmoothed[fi]);";
+        print "      for(int fi=0;fi<60;fi++)fprintf(fm,\"gapprob %d %ld\\n\",fi,gapProbs[fi]);";
+        print "      fclose(fm);} }";
+        mdone = 1;
+    }
     print;
 }
