@@ -1,0 +1,681 @@
+// fb_engine.cu -- the CUDA (sm_100a) engine behind include/figbird_b200.h.
+//
+// One CTA owns one work item = one (gap, candidate length) and runs the whole EM chain of that item on
+// chip: initialisation from the partial-read pile-ups, then per round pass 1 (weighted votes), soft
+// consensus, pass 2 (hard placement against the consensus), hard consensus / coverage, comp_count and the
+// M-step, with the row tables (P, E, counts) resident in shared memory.  Reference arithmetic:
+//   placeReads          Figbird.cpp:3022-4387     computeProbsGap / computeErrorProbsGap  :2090-2137
+//   computeSequence     Figbird.cpp:4417-4508     update_partial_prob (initial gap rows)   :1913-2088
+//
+// Numerics.  The filled sequence must equal the reference's, so every product is formed in the reference's
+// order with separately rounded IEEE operations (__dmul_rn/__dadd_rn/__ddiv_rn are never contracted to FMA;
+// x86-64 g++ emits none either).  Per-read maxima are returned as raw products so that the host applies
+// glibc's log/log10 exactly as the reference does; the accept test -log10(p) < cutoff is turned into
+// p >= accept_min_p with a threshold found by bisection on glibc's log10 at model upload.  Only the soft
+// weights (exp / pow of device logs) and the summation order of the votes differ from the CPU, at the
+// 1e-15 relative level; the vote reduction is a fixed-order gather, so results are run-to-run deterministic.
+//
+// Mapping.  Pass 1/2 work unit = (read, 32 consecutive offsets): one warp, lane = offset, all lanes walk
+// the same read base j, so read codes and error-model entries are warp-uniform and table rows are
+// consecutive across lanes (conflict-free 8-byte shared loads).  Weights of a chunk of reads are parked in
+// shared memory (W), then gathered per gap row in fixed order into the count matrices -- no atomics on
+// doubles.  There is no CPU path in this file: without a device fb_ctx_create fails.
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/figbird_b200.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxSmem = 200 * 1024;      // dynamic shared memory we opt in to (227 KB is the sm_100 limit)
+constexpr int kMinW = 16 * 1024;          // least W-buffer bytes we accept before moving tables to global
+
+struct DevGap { long long gap_start; int mode, orig_len, n_reads, read_begin, flank_len, flank_begin, pile_len, pile_begin; };
+
+struct DevItem {
+    int kind, gap, Lg, max_rounds, flags, comp_in;
+    int n_slots, tables_in_smem, max_len, pad_;
+    long long counts_in_off, string_in_off;     // byte offsets into the input arena (-1: none)
+    long long out_off;                           // byte offset of the FbItemOut header in the output arena
+    long long scratch_off;                       // byte offset of this item's global table scratch (-1: tables in smem)
+    long long off_p1, off_p2, off_pos, off_soft, off_hard, off_cov, off_counts;   // relative to out_off
+};
+
+struct DevModel {
+    const double* e; const double* ome; const double* match; const double* mism;   // [k], [k], [k], [k][25]
+    const double* pdf; int n_insert;
+    double etp[25];
+    int tmin, tmax, max_read_len;
+    double accept_min_p;
+};
+
+struct Params {
+    DevModel m;
+    const DevGap* gaps;
+    const int* read_len; const long long* read_off; const int* read_mate;
+    const unsigned char* read_flags; const unsigned char* read_jlo; const unsigned char* read_jcut; const unsigned char* codes;
+    const unsigned char* flank; const int* pile_l; const int* pile_r;
+    const DevItem* items;
+    const unsigned char* in_arena; unsigned char* out_arena; unsigned char* scratch;
+    unsigned long long* counters;   // [0] pass-1 placements, [1] pass-2 placements, [2] base terms
+    int smem_bytes;
+};
+
+__device__ __forceinline__ bool admissible(const DevModel& m, const DevGap& g, int fl, int rel, int len, int x0, int Lg, bool finalizeRef, int* tOut) {
+    const long long off = (long long)Lg - g.orig_len;
+    bool apply; long long t;
+    if (g.mode == FB_MODE_UNMAPPED) { apply = true; t = (fl & FB_READ_LEFT) ? ((long long)x0 - rel + len) : ((long long)rel + off + len - x0); }
+    else if (fl & FB_READ_LEFT) { apply = !(fl & FB_READ_NOMATE); t = (long long)x0 - rel + len; }
+    else {
+        long long absref;
+        if (fl & FB_READ_NOMATE) { if (!finalizeRef) { *tOut = 0; return true; } absref = -1 + off; }
+        else absref = (long long)rel + g.gap_start + off;
+        apply = (absref != -1);
+        t = (absref - g.gap_start) + len - x0;
+    }
+    *tOut = (int)t;
+    if (apply && (t < m.tmin || t > m.tmax)) return false;
+    return true;
+}
+
+__device__ __forceinline__ void window(const DevGap& g, int fl, int len, int Lg, int* lo, int* hi) {
+    if (g.mode == FB_MODE_UNMAPPED) { *lo = -(len - 1); *hi = Lg - 1; }
+    else if (fl & FB_READ_LEFT) { *lo = -(len - 1); *hi = -1; }
+    else { *lo = Lg - len + 1; *hi = Lg - 1; }
+}
+
+// E[j] = sum_{k<4, k!=j} P[k]*ETP[k][j] in k order (Figbird.cpp:2118-2137)
+__device__ __forceinline__ void errRow(const double* etp, const double p[4], double e[5]) {
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { if (j == k) continue; s = __dadd_rn(s, __dmul_rn(p[k], etp[k * 5 + j])); }
+        e[j] = s;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) fb_em_kernel(const Params prm) {
+    const DevItem it = prm.items[blockIdx.x];
+    const DevGap g = prm.gaps[it.gap];
+    const DevModel& m = prm.m;
+    const int Lg = it.Lg, F = g.flank_len, rows = Lg + 2 * F, R = g.n_reads;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_comp, s_same, s_stop, s_flags;
+    __shared__ unsigned long long s_place1, s_place2, s_terms;
+
+    // ---- carve the row tables (shared memory, or this item's global scratch when they do not fit)
+    unsigned char* tb = it.tables_in_smem ? smem_raw : (prm.scratch + it.scratch_off);
+    double* P = (double*)tb;                 // [4][rows]
+    double* E = P + 4 * (size_t)rows;        // [5][rows]
+    double* C = E + 5 * (size_t)rows;        // [5][Lg]   countsGap gap rows
+    int* NC = (int*)(C + 5 * (size_t)Lg);    // [5][Lg]   new_counts_gap gap rows
+    unsigned char* G = (unsigned char*)(NC + 5 * (size_t)Lg);   // [rows] gapString codes
+    unsigned char* PREV = G + rows;          // [Lg] previous hard consensus
+    size_t tbBytes = ((size_t)(PREV + Lg - tb) + 15) & ~(size_t)15;
+    double* W = (double*)(it.tables_in_smem ? smem_raw + tbBytes : smem_raw);
+    const int wCap = (int)((prm.smem_bytes - (it.tables_in_smem ? tbBytes : 0)) / sizeof(double));
+
+    unsigned char* out = prm.out_arena + it.out_off;
+    double* oP1 = (double*)(out + it.off_p1);
+    double* oP2 = (double*)(out + it.off_p2);
+    int* oPos = (int*)(out + it.off_pos);
+    unsigned char* oSoft = out + it.off_soft;
+    unsigned char* oHard = out + it.off_hard;
+    int* oCov = (int*)(out + it.off_cov);
+
+    const unsigned char* lf = prm.flank + g.flank_begin;
+    const unsigned char* rf = lf + F;
+    const bool unm = (g.mode == FB_MODE_UNMAPPED);
+
+    if (tid == 0) { s_comp = 0; s_stop = 0; s_flags = 0; s_place1 = 0; s_place2 = 0; s_terms = 0; }
+
+    // ---- gapString flanks
+    for (int r = tid; r < rows; r += kThreads) {
+        unsigned char c = 4;
+        if (r < F) c = lf[r]; else if (r >= F + Lg) c = rf[r - F - Lg];
+        G[r] = c;
+    }
+    int prevValid = 0;   // previous hard consensus present (uniform)
+
+    if (it.kind == FB_ITEM_EM) {
+        // flank rows: one-hot counts -> P, E (initialize + computeProbsGap, Figbird.cpp:2342-2372, 2090-2109)
+        for (int r = tid; r < rows; r += kThreads) {
+            if (r >= F && r < F + Lg) continue;
+            const int f = (r < F) ? lf[r] : rf[r - F - Lg];
+            double p[4], e[5];
+#pragma unroll
+            for (int k = 0; k < 4; k++) p[k] = (f == 4) ? 0.25 : (f == k ? 1.0 : 0.0);
+            errRow(m.etp, p, e);
+#pragma unroll
+            for (int k = 0; k < 4; k++) P[(size_t)k * rows + r] = p[k];
+#pragma unroll
+            for (int k = 0; k < 5; k++) E[(size_t)k * rows + r] = e[k];
+        }
+        if (it.flags & FB_FLAG_RESUME) {
+            const double* cin = (const double*)(prm.in_arena + it.counts_in_off);
+            for (int i = tid; i < 5 * Lg; i += kThreads) { int x = i / 5, k = i % 5; C[(size_t)k * Lg + x] = cin[i]; }
+            if (it.string_in_off >= 0) { const unsigned char* sin = prm.in_arena + it.string_in_off; for (int x = tid; x < Lg; x += kThreads) PREV[x] = sin[x]; prevValid = 1; }
+            if (tid == 0) s_comp = it.comp_in;
+        } else {
+            // gap rows from the partial pile-ups (update_partial_prob, Figbird.cpp:2039-2081)
+            const int* pl = prm.pile_l + 4 * (size_t)g.pile_begin; const int* pr = prm.pile_r + 4 * (size_t)g.pile_begin;
+            for (int x = tid; x < Lg; x += kThreads) {
+                double cnt[4]; int tot = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    int c = 1;
+                    if (x < g.pile_len) c += pl[4 * x + k];
+                    int u = Lg - 1 - x; if (u < g.pile_len) c += pr[4 * u + k];
+                    cnt[k] = (double)c; tot += c;
+                }
+                double p[4], e[5];
+#pragma unroll
+                for (int k = 0; k < 4; k++) p[k] = __ddiv_rn(cnt[k], (double)tot);
+                errRow(m.etp, p, e);
+#pragma unroll
+                for (int k = 0; k < 4; k++) P[(size_t)k * rows + F + x] = p[k];
+#pragma unroll
+                for (int k = 0; k < 5; k++) E[(size_t)k * rows + F + x] = e[k];
+            }
+        }
+    } else {
+        const unsigned char* sin = prm.in_arena + it.string_in_off;
+        for (int x = tid; x < Lg; x += kThreads) { unsigned char c = it.string_in_off >= 0 ? sin[x] : 4; G[F + x] = c; oSoft[x] = c; oHard[x] = 4; oCov[x] = 0; }
+        for (int q = tid; q < R; q += kThreads) oP1[q] = -1.0;
+    }
+    __syncthreads();
+
+    // M-step over the gap rows (flank rows never change): computeProbsGap(0) + computeErrorProbsGap
+    auto mstep = [&]() {
+        for (int x = tid; x < Lg; x += kThreads) {
+            double c[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) c[k] = C[(size_t)k * Lg + x];
+            double total = 0;
+#pragma unroll
+            for (int k = 0; k < 5; k++) total = __dadd_rn(total, c[k]);
+            const double nq = __ddiv_rn(c[4], 4.0);
+            double p[4], e[5];
+#pragma unroll
+            for (int k = 0; k < 4; k++) p[k] = (total != 0.0) ? __ddiv_rn(__dadd_rn(c[k], nq), total) : 0.25;
+            errRow(m.etp, p, e);
+#pragma unroll
+            for (int k = 0; k < 4; k++) P[(size_t)k * rows + F + x] = p[k];
+#pragma unroll
+            for (int k = 0; k < 5; k++) E[(size_t)k * rows + F + x] = e[k];
+        }
+    };
+    if (it.kind == FB_ITEM_EM && (it.flags & FB_FLAG_RESUME)) { mstep(); __syncthreads(); }
+
+    // ---- read chunking: W holds [reads of the chunk][stride] doubles
+    const int maxLen = it.max_len;
+    const int stride = unm ? (maxLen + Lg - 1) : (maxLen - 1);
+    const int strideP = max(stride, 1);
+    const int chunkReads = max(1, wCap / strideP);
+    const int cpr = (strideP + 31) / 32;     // 32-offset units per read
+
+    // pass-2 style scoring of reads [q0,q1) into W, then per-read first-max
+    auto pass2 = [&](int slot, bool finalizeRef, bool vote) {
+        for (int q0 = 0; q0 < R; q0 += chunkReads) {
+            const int q1 = min(R, q0 + chunkReads);
+            const int units = (q1 - q0) * cpr;
+            for (int u = warp; u < units; u += kWarps) {
+                const int ql = u / cpr, ch = u - ql * cpr;
+                const int qi = g.read_begin + q0 + ql;
+                const int len = prm.read_len[qi], fl = prm.read_flags[qi], rel = prm.read_mate[qi];
+                const unsigned char* rd = prm.codes + prm.read_off[qi];
+                const int jlo = prm.read_jlo[qi], jhi = len - prm.read_jcut[qi];
+                int lo, hi; window(g, fl, len, Lg, &lo, &hi);
+                const int x0 = lo + ch * 32 + lane;
+                double p = -1.0;
+                int t;
+                const bool act = (x0 <= hi) && (strideP > ch * 32 + lane) && admissible(m, g, fl, rel, len, x0, Lg, finalizeRef, &t);
+                if (act) {
+                    p = 1.0;
+                    const bool rev = fl & FB_READ_REVERSE;
+                    const unsigned char* gs = G + (x0 + F);
+                    for (int j = jlo; j < jhi; j++) {
+                        const int to = rd[j], from = gs[j];
+                        const int k = rev ? (len - j - 1) : j;
+                        const double f = (from == to) ? m.match[k] : m.mism[k * 25 + from * 5 + to];
+                        p = __dmul_rn(p, f);
+                    }
+                }
+                const unsigned act_mask = __ballot_sync(0xffffffffu, act);
+                if (lane == 0 && act_mask) { atomicAdd(&s_place2, (unsigned long long)__popc(act_mask)); atomicAdd(&s_terms, (unsigned long long)__popc(act_mask) * (unsigned long long)(jhi - jlo)); }
+                if (ch * 32 + lane < strideP) W[(size_t)ql * strideP + ch * 32 + lane] = p;
+            }
+            __syncthreads();
+            // first maximum over ascending offsets (strict >), accept test, unit votes (Figbird.cpp:3787-3912)
+            for (int ql = warp; ql < q1 - q0; ql += kWarps) {
+                const int q = q0 + ql, qi = g.read_begin + q;
+                const int len = prm.read_len[qi], fl = prm.read_flags[qi];
+                int lo, hi; window(g, fl, len, Lg, &lo, &hi);
+                const int n = hi - lo + 1;
+                double best = -1.0; int bestI = 0x7fffffff;
+                for (int i = lane; i < n; i += 32) { double v = W[(size_t)ql * strideP + i]; if (v > best) { best = v; bestI = i; } }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    double ov = __shfl_xor_sync(0xffffffffu, best, o); int oi = __shfl_xor_sync(0xffffffffu, bestI, o);
+                    if (ov > best || (ov == best && oi < bestI)) { best = ov; bestI = oi; }
+                }
+                const int bestx = (best >= 0) ? lo + bestI : 0;
+                if (lane == 0) { oP2[(size_t)slot * R + q] = best; oPos[(size_t)slot * R + q] = bestx; }
+                if (vote && unm && best >= m.accept_min_p) {
+                    const unsigned char* rd = prm.codes + prm.read_off[qi];
+                    for (int j = lane; j < len; j += 32) { int x = bestx + j; if (x >= 0 && x < Lg) atomicAdd(&NC[(size_t)rd[j] * Lg + x], 1); }
+                    if (lane == 0 && g.orig_len <= 30) {
+                        int fo = 0; const int p0 = bestx, val = p0 + len - Lg;
+                        if (p0 < 0 && val > 0 && -p0 > 3 && val > 3) fo |= 4;
+                        if (p0 < 0 && p0 + len > 0 && -p0 > 3) fo |= 1;
+                        if (p0 > 0 && p0 < Lg && val > 0 && val > 3) fo |= 2;
+                        if (fo) atomicOr(&s_flags, fo);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    };
+
+    int calls = 0;
+    if (it.kind == FB_ITEM_HARD) {
+        pass2(0, (it.flags & FB_FLAG_FINALIZE_REF) != 0, false);
+        calls = 1;
+    } else {
+        const int maxCalls = it.max_rounds + ((it.flags & FB_FLAG_EXTRA_PASS) ? 1 : 0);
+        bool emDone = it.max_rounds <= 0;
+        for (int call = 0; call < maxCalls; call++) {
+            const bool extra = emDone;
+            const int slot = (it.flags & FB_FLAG_RECORD_ALL) ? call : 0;
+            for (int i = tid; i < 5 * Lg; i += kThreads) { C[i] = 0.0; NC[i] = 0; }
+            for (int q = tid; q < R; q += kThreads) oP1[(size_t)slot * R + q] = 0.0;   // bit pattern 0 == "no admissible offset yet"
+            __syncthreads();
+            // ================= pass 1 (Figbird.cpp:3082-3263, 3530-3689) =================
+            for (int q0 = 0; q0 < R; q0 += chunkReads) {
+                const int q1 = min(R, q0 + chunkReads);
+                const int units = (q1 - q0) * cpr;
+                for (int u = warp; u < units; u += kWarps) {
+                    const int ql = u / cpr, ch = u - ql * cpr;
+                    const int qi = g.read_begin + q0 + ql;
+                    const int len = prm.read_len[qi], fl = prm.read_flags[qi], rel = prm.read_mate[qi];
+                    const unsigned char* rd = prm.codes + prm.read_off[qi];
+                    const int jlo = prm.read_jlo[qi], jhi = len - prm.read_jcut[qi];
+                    int lo, hi; window(g, fl, len, Lg, &lo, &hi);
+                    const int x0 = lo + ch * 32 + lane;
+                    int t;
+                    const bool act = (x0 <= hi) && (strideP > ch * 32 + lane) && admissible(m, g, fl, rel, len, x0, Lg, false, &t);
+                    double w = 0.0, p = 0.0;
+                    if (act) {
+                        p = unm ? m.pdf[min(max(t, 0), m.n_insert - 1)] : 1.0;
+                        const bool rev = fl & FB_READ_REVERSE;
+                        const double* Pr = P + (x0 + F);
+                        const double* Er = E + (x0 + F);
+                        for (int j = jlo; j < jhi; j++) {
+                            const int c = rd[j];
+                            const int k = rev ? (len - 1 - j) : j;
+                            const double ek = m.e[k];
+                            double term;
+                            if (c < 4) term = __dadd_rn(__dmul_rn(Pr[(size_t)c * rows + j], m.ome[k]), __dmul_rn(ek, Er[(size_t)c * rows + j]));
+                            else term = __dmul_rn(ek, Er[(size_t)4 * rows + j]);
+                            p = __dmul_rn(p, term);
+                        }
+                        if (p > 0.0) {
+                            if (unm) { const double s = log10(p); w = exp(0.5 * s); }     // Figbird.cpp:3591,3601
+                            else { const double s = log(p); w = pow(10.0, s); }           // Figbird.cpp:3169,3179
+                        } else p = 0.0;
+                    }
+                    // per-read maximum of the raw product (positive doubles order like their bit patterns)
+                    double pm = p;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) pm = fmax(pm, __shfl_xor_sync(0xffffffffu, pm, o));
+                    const unsigned act_mask = __ballot_sync(0xffffffffu, act);
+                    if (lane == 0 && act_mask) {
+                        if (pm > 0.0) atomicMax((unsigned long long*)&oP1[(size_t)slot * R + q0 + ql], (unsigned long long)__double_as_longlong(pm));
+                        atomicAdd(&s_place1, (unsigned long long)__popc(act_mask));
+                        atomicAdd(&s_terms, (unsigned long long)__popc(act_mask) * (unsigned long long)(jhi - jlo));
+                    }
+                    if (ch * 32 + lane < strideP) W[(size_t)ql * strideP + ch * 32 + lane] = w;
+                }
+                __syncthreads();
+                // gather the weights of this chunk into the gap rows, fixed order: read ascending, read base ascending
+                for (int x = tid; x < Lg; x += kThreads) {
+                    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+                    for (int ql = 0; ql < q1 - q0; ql++) {
+                        const int qi = g.read_begin + q0 + ql;
+                        const int len = prm.read_len[qi], fl = prm.read_flags[qi];
+                        const unsigned char* rd = prm.codes + prm.read_off[qi];
+                        int lo, hi; window(g, fl, len, Lg, &lo, &hi);
+                        // x0 = x - j in [lo, hi]  <=>  j in [x - hi, x - lo]
+                        const int ja = max(0, x - hi), jb = min(len - 1, x - lo);
+                        const double* wr = W + (size_t)ql * strideP - lo;
+                        for (int j = ja; j <= jb; j++) {
+                            const double w = wr[x - j];
+                            switch (rd[j]) { case 0: a0 = __dadd_rn(a0, w); break; case 1: a1 = __dadd_rn(a1, w); break; case 2: a2 = __dadd_rn(a2, w); break; case 3: a3 = __dadd_rn(a3, w); break; default: a4 = __dadd_rn(a4, w); }
+                        }
+                    }
+                    C[x] = __dadd_rn(C[x], a0); C[(size_t)Lg + x] = __dadd_rn(C[(size_t)Lg + x], a1); C[(size_t)2 * Lg + x] = __dadd_rn(C[(size_t)2 * Lg + x], a2);
+                    C[(size_t)3 * Lg + x] = __dadd_rn(C[(size_t)3 * Lg + x], a3); C[(size_t)4 * Lg + x] = __dadd_rn(C[(size_t)4 * Lg + x], a4);
+                }
+                __syncthreads();
+            }
+            // pass-1 maxima: bit pattern 0 means no admissible offset -> -1
+            for (int q = tid; q < R; q += kThreads) { double v = oP1[(size_t)slot * R + q]; if (!(v > 0.0)) oP1[(size_t)slot * R + q] = -1.0; }
+            // ================= computeSequence(0,0) =================
+            for (int x = tid; x < Lg; x += kThreads) {
+                double mx = 0; int mi = -1;
+#pragma unroll
+                for (int k = 0; k < 5; k++) { double v = C[(size_t)k * Lg + x]; if (v > mx) { mx = v; mi = k; } }
+                unsigned char c = (mi >= 0 && mi < 4) ? (unsigned char)mi : 4;
+                G[F + x] = c; oSoft[x] = c;
+            }
+            __syncthreads();
+            // ================= pass 2 =================
+            pass2(slot, false, true);
+            // ================= computeSequence(1,1) + comp_count (Figbird.cpp:3916-3927) =================
+            if (unm) {
+                if (tid == 0) s_same = 1;
+                __syncthreads();
+                int same = prevValid;
+                for (int x = tid; x < Lg; x += kThreads) {
+                    int mx = 0, mi = -1;
+#pragma unroll
+                    for (int k = 0; k < 5; k++) { int v = NC[(size_t)k * Lg + x]; if (v > mx) { mx = v; mi = k; } }
+                    unsigned char h = (mx > 0 && mi >= 0 && mi < 4) ? (unsigned char)mi : 4;
+                    oHard[x] = h; oCov[x] = mx;
+                    if (!prevValid || PREV[x] != h) same = 0;
+                    PREV[x] = h;
+                }
+                if (!same && Lg > 0) s_same = 0;   // benign race: all writers store 0
+                __syncthreads();
+                // an empty previous string equals the new one only when Lg == 0
+                const int equal = (Lg == 0) ? 1 : (prevValid && s_same);
+                if (tid == 0) s_comp = equal ? s_comp + 1 : 0;
+                prevValid = 1;
+            } else {
+                for (int x = tid; x < Lg; x += kThreads) { oHard[x] = 4; oCov[x] = 0; }
+            }
+            calls++;
+            __syncthreads();
+            if (extra) break;
+            // ================= M-step =================
+            mstep();
+            if (unm && !(it.flags & FB_FLAG_NO_COMP_STOP) && s_comp >= 5) emDone = true;
+            if (call + 1 >= it.max_rounds) emDone = true;
+            __syncthreads();
+            if (emDone && !(it.flags & FB_FLAG_EXTRA_PASS)) break;
+        }
+        if (it.off_counts >= 0) {
+            double* oc = (double*)(out + it.off_counts);
+            for (int i = tid; i < 5 * Lg; i += kThreads) { int x = i / 5, k = i % 5; oc[i] = C[(size_t)k * Lg + x]; }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        FbItemOut* H = (FbItemOut*)out;
+        H->calls = calls; H->comp_count = s_comp; H->flags = s_flags; H->placements = (long long)s_place1;
+        atomicAdd(&prm.counters[0], s_place1); atomicAdd(&prm.counters[1], s_place2); atomicAdd(&prm.counters[2], s_terms);
+    }
+}
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { c->err = std::string(#x) + ": " + cudaGetErrorString(e_); return FB_ERR_CUDA; } } while (0)
+
+template <class T> struct DevBuf {
+    T* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t n) { if (n <= cap) return cudaSuccess; if (p) cudaFree(p); p = nullptr; cap = 0; size_t want = n + n / 4 + 64; cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T)); if (e == cudaSuccess) cap = want; return e; }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct fb_ctx {
+    int device = 0;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int smemOptin = 0;
+    bool haveModel = false, haveBatch = false;
+    DevModel dm{};
+    DevBuf<double> d_e, d_ome, d_match, d_mism, d_pdf;
+    std::vector<DevGap> hGaps; std::vector<int> hGapMaxLen;
+    DevBuf<DevGap> d_gaps; DevBuf<int> d_rlen, d_rmate, d_pl, d_pr; DevBuf<long long> d_roff;
+    DevBuf<unsigned char> d_rfl, d_jlo, d_jcut, d_codes, d_flank;
+    DevBuf<DevItem> d_items; DevBuf<unsigned char> d_in, d_out, d_scratch;
+    DevBuf<unsigned long long> d_ctr;
+    unsigned char* h_out = nullptr; size_t h_out_cap = 0;     // pinned result arena
+    unsigned char* h_in = nullptr; size_t h_in_cap = 0;       // pinned staging for items + inputs
+    FbCounters ctr{};
+};
+
+extern "C" const char* fb_engine_name(void) { return "cuda-sm100a"; }
+extern "C" const char* fb_last_error(const fb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+extern "C" fb_status fb_ctx_create(int32_t device, fb_ctx** out) {
+    if (!out) return FB_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return FB_ERR_NODEVICE;
+    fb_ctx* c = new fb_ctx();
+    c->device = device;
+    *out = c;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, device));
+    if (pr.major < 10) { c->err = "device is not sm_100-class (this library is built for sm_100a only)"; return FB_ERR_NODEVICE; }
+    c->smemOptin = (int)pr.sharedMemPerBlockOptin;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
+    CK(cudaFuncSetAttribute(fb_em_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CK(c->d_ctr.ensure(4)); CK(cudaMemset(c->d_ctr.p, 0, 4 * sizeof(unsigned long long)));
+    return FB_OK;
+}
+
+extern "C" void fb_ctx_destroy(fb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    c->d_e.release(); c->d_ome.release(); c->d_match.release(); c->d_mism.release(); c->d_pdf.release();
+    c->d_gaps.release(); c->d_rlen.release(); c->d_rmate.release(); c->d_pl.release(); c->d_pr.release(); c->d_roff.release();
+    c->d_rfl.release(); c->d_jlo.release(); c->d_jcut.release(); c->d_codes.release(); c->d_flank.release();
+    c->d_items.release(); c->d_in.release(); c->d_out.release(); c->d_scratch.release(); c->d_ctr.release();
+    if (c->h_out) cudaFreeHost(c->h_out);
+    if (c->h_in) cudaFreeHost(c->h_in);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+template <class T> static fb_status upload(fb_ctx* c, DevBuf<T>& b, const T* src, size_t n) {
+    CK(b.ensure(n ? n : 1));
+    if (n) { CK(cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, c->stream)); c->ctr.h2d_bytes += (int64_t)(n * sizeof(T)); }
+    return FB_OK;
+}
+
+extern "C" fb_status fb_model_upload(fb_ctx* c, const FbModel* m) {
+    if (!c || !m || m->max_read_len <= 0 || m->n_insert <= 0) return FB_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    const int RL = m->max_read_len;
+    std::vector<double> ome(RL), match(RL), mism((size_t)RL * 25);
+    for (int k = 0; k < RL; k++) {
+        ome[k] = 1 - m->err_pos[k];
+        match[k] = 1 - m->err_pos[k] - m->ins_pos[k] - m->del_pos[k];                 // Figbird.cpp:3400
+        for (int f = 0; f < 5; f++) for (int t = 0; t < 5; t++) mism[(size_t)k * 25 + f * 5 + t] = m->err_pos[k] * m->err_type[f * 5 + t];   // :3405
+    }
+    fb_status s;
+    if ((s = upload(c, c->d_e, m->err_pos, RL))) return s;
+    if ((s = upload(c, c->d_ome, ome.data(), RL))) return s;
+    if ((s = upload(c, c->d_match, match.data(), RL))) return s;
+    if ((s = upload(c, c->d_mism, mism.data(), mism.size()))) return s;
+    if ((s = upload(c, c->d_pdf, m->insert_pdf, m->n_insert))) return s;
+    CK(cudaStreamSynchronize(c->stream));
+    c->dm.e = c->d_e.p; c->dm.ome = c->d_ome.p; c->dm.match = c->d_match.p; c->dm.mism = c->d_mism.p; c->dm.pdf = c->d_pdf.p; c->dm.n_insert = m->n_insert;
+    memcpy(c->dm.etp, m->err_type, sizeof c->dm.etp);
+    c->dm.tmin = m->insert_min; c->dm.tmax = m->insert_max; c->dm.max_read_len = RL;
+    // accept iff -log10(p) < cutoff (Figbird.cpp:3474,3852).  log10 is monotone, so the accepted set is
+    // {p >= T}; find T = the smallest double glibc accepts, by bisection on the bit pattern.
+    {
+        const double cut = (double)m->prob_cutoff;
+        auto acc = [&](double p) { return -log10(p) < cut; };
+        double lo = pow(10.0, -cut) * 0.5, hi = pow(10.0, -cut) * 2.0;
+        if (!(lo > 0)) lo = DBL_TRUE_MIN;
+        if (acc(lo)) c->dm.accept_min_p = lo;        // cutoff so large that everything positive passes in range
+        else if (!acc(hi)) c->dm.accept_min_p = hi;  // degenerate; keep monotone behaviour
+        else {
+            unsigned long long a, b; memcpy(&a, &lo, 8); memcpy(&b, &hi, 8);
+            while (b - a > 1) { unsigned long long mid = a + (b - a) / 2; double pm; memcpy(&pm, &mid, 8); if (acc(pm)) b = mid; else a = mid; }
+            double t; memcpy(&t, &b, 8); c->dm.accept_min_p = t;
+        }
+        if (m->prob_cutoff <= 0) c->dm.accept_min_p = INFINITY;   // -log10(p) < 0 needs p > 1: never for a probability
+    }
+    c->haveModel = true;
+    return FB_OK;
+}
+
+extern "C" fb_status fb_batch_upload(fb_ctx* c, const FbGapBatch* b) {
+    if (!c || !b || b->n_gaps < 0) return FB_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    c->hGaps.resize(b->n_gaps); c->hGapMaxLen.assign(b->n_gaps, 1);
+    for (int i = 0; i < b->n_gaps; i++) {
+        const FbGap& g = b->gaps[i];
+        DevGap d{}; d.gap_start = g.gap_start; d.mode = g.mode; d.orig_len = g.orig_len; d.n_reads = g.n_reads; d.read_begin = g.read_begin;
+        d.flank_len = g.flank_len; d.flank_begin = g.flank_begin; d.pile_len = g.pile_len; d.pile_begin = g.pile_begin;
+        c->hGaps[i] = d;
+        int ml = 1;
+        for (int q = 0; q < g.n_reads; q++) {
+            int len = b->read_len[g.read_begin + q];
+            if (len > g.flank_len + 1) { c->err = "flank_len must be >= read length - 1"; return FB_ERR_ARG; }
+            if (len > 255) { c->err = "read longer than 255 bases"; return FB_ERR_ARG; }
+            ml = len > ml ? len : ml;
+        }
+        c->hGapMaxLen[i] = ml;
+    }
+    fb_status s;
+    if ((s = upload(c, c->d_gaps, c->hGaps.data(), c->hGaps.size()))) return s;
+    if ((s = upload(c, c->d_rlen, b->read_len, (size_t)b->n_reads))) return s;
+    if ((s = upload(c, c->d_rmate, b->read_mate, (size_t)b->n_reads))) return s;
+    { std::vector<long long> ro(b->read_code_off, b->read_code_off + b->n_reads); if ((s = upload(c, c->d_roff, ro.data(), ro.size()))) return s; CK(cudaStreamSynchronize(c->stream)); }
+    if ((s = upload(c, c->d_rfl, b->read_flags, (size_t)b->n_reads))) return s;
+    if ((s = upload(c, c->d_jlo, b->read_jlo, (size_t)b->n_reads))) return s;
+    if ((s = upload(c, c->d_jcut, b->read_jcut, (size_t)b->n_reads))) return s;
+    if ((s = upload(c, c->d_codes, b->read_codes, (size_t)b->n_codes))) return s;
+    if ((s = upload(c, c->d_flank, b->flank_codes, (size_t)b->n_flank))) return s;
+    if ((s = upload(c, c->d_pl, b->pile_left, (size_t)b->n_pile_rows * 4))) return s;
+    if ((s = upload(c, c->d_pr, b->pile_right, (size_t)b->n_pile_rows * 4))) return s;
+    CK(cudaStreamSynchronize(c->stream));
+    c->haveBatch = true;
+    return FB_OK;
+}
+
+extern "C" fb_status fb_get_counters(const fb_ctx* c, FbCounters* out) {
+    if (!c || !out) return FB_ERR_ARG;
+    *out = c->ctr;
+    return FB_OK;
+}
+
+extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, const FbItemOut** out) {
+    if (!c || !items || !out || n < 0) return FB_ERR_ARG;
+    if (!c->haveModel || !c->haveBatch) { c->err = "model/batch not uploaded"; return FB_ERR_STATE; }
+    if (n == 0) return FB_OK;
+    CK(cudaSetDevice(c->device));
+    auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    std::vector<DevItem> di(n);
+    size_t outTotal = 0, inTotal = 0, scratchTotal = 0;
+    int smemNeed = kMinW;
+    for (int i = 0; i < n; i++) {
+        const FbWorkItem& it = items[i];
+        if (it.gap < 0 || it.gap >= (int)c->hGaps.size() || it.cand_len < 0) { c->err = "bad work item"; return FB_ERR_ARG; }
+        const DevGap& g = c->hGaps[it.gap];
+        DevItem d{};
+        d.kind = it.kind; d.gap = it.gap; d.Lg = it.cand_len; d.max_rounds = it.max_rounds; d.flags = it.flags; d.comp_in = it.comp_count_in;
+        const int Lg = it.cand_len, R = g.n_reads, rows = Lg + 2 * g.flank_len;
+        int slots = 1;
+        if (it.kind == FB_ITEM_EM && (it.flags & FB_FLAG_RECORD_ALL)) slots = it.max_rounds + ((it.flags & FB_FLAG_EXTRA_PASS) ? 1 : 0);
+        d.n_slots = slots;
+        d.out_off = (long long)outTotal;
+        size_t o = al(sizeof(FbItemOut));
+        d.off_p1 = o; o += al(sizeof(double) * slots * R);
+        d.off_p2 = o; o += al(sizeof(double) * slots * R);
+        d.off_pos = o; o += al(sizeof(int) * slots * R);
+        d.off_soft = o; o += al(Lg);
+        d.off_hard = o; o += al(Lg);
+        d.off_cov = o; o += al(sizeof(int) * Lg);
+        if (it.flags & FB_FLAG_WANT_COUNTS) { d.off_counts = o; o += al(sizeof(double) * 5 * Lg); } else d.off_counts = -1;
+        outTotal += o;
+        d.counts_in_off = -1; d.string_in_off = -1;
+        if (it.kind == FB_ITEM_EM && (it.flags & FB_FLAG_RESUME)) {
+            if (!it.counts_in) { c->err = "RESUME item without counts_in"; return FB_ERR_ARG; }
+            d.counts_in_off = (long long)inTotal; inTotal += al(sizeof(double) * 5 * Lg);
+        }
+        if (it.string_in && Lg > 0) { d.string_in_off = (long long)inTotal; inTotal += al(Lg); }
+        // shared-memory plan: tables if they leave >= kMinW for W, else global scratch
+        const size_t tb = al((size_t)rows * 9 * 8 + (size_t)Lg * 5 * 8 + (size_t)Lg * 5 * 4 + rows + Lg);
+        const int ml = c->hGapMaxLen[it.gap];
+        d.max_len = ml;
+        const size_t stride = (g.mode == FB_MODE_UNMAPPED) ? (size_t)(ml + Lg - 1) : (size_t)(ml - 1);
+        const size_t wWant = std::min<size_t>(std::max<size_t>(stride, 1) * 8 * (size_t)std::max(R, 1), 96 * 1024);
+        if (tb + kMinW <= (size_t)kMaxSmem) {
+            d.tables_in_smem = 1; d.scratch_off = -1;
+            smemNeed = std::max<int>(smemNeed, (int)std::min<size_t>(kMaxSmem, tb + std::max<size_t>(wWant, kMinW)));
+        } else {
+            d.tables_in_smem = 0; d.scratch_off = (long long)scratchTotal; scratchTotal += tb;
+            smemNeed = std::max<int>(smemNeed, (int)std::min<size_t>(kMaxSmem, std::max<size_t>(wWant, std::max<size_t>(stride, 1) * 8 + 64)));
+            if (std::max<size_t>(stride, 1) * 8 > (size_t)kMaxSmem) { c->err = "candidate length too large for one weight row in shared memory"; return FB_ERR_ARG; }
+        }
+        di[i] = d;
+    }
+    // ---- stage inputs
+    const size_t itemsBytes = al(sizeof(DevItem) * (size_t)n);
+    const size_t inBytes = itemsBytes + inTotal + 16;
+    if (inBytes > c->h_in_cap) { if (c->h_in) cudaFreeHost(c->h_in); c->h_in = nullptr; c->h_in_cap = 0; size_t want = inBytes + inBytes / 2; CK(cudaMallocHost((void**)&c->h_in, want)); c->h_in_cap = want; }
+    memcpy(c->h_in, di.data(), sizeof(DevItem) * (size_t)n);
+    for (int i = 0; i < n; i++) {
+        const FbWorkItem& it = items[i];
+        if (di[i].counts_in_off >= 0) memcpy(c->h_in + itemsBytes + di[i].counts_in_off, it.counts_in, sizeof(double) * 5 * (size_t)it.cand_len);
+        if (di[i].string_in_off >= 0) memcpy(c->h_in + itemsBytes + di[i].string_in_off, it.string_in, (size_t)it.cand_len);
+    }
+    CK(c->d_in.ensure(inBytes));
+    CK(c->d_out.ensure(outTotal + 16));
+    CK(c->d_scratch.ensure(scratchTotal + 16));
+    if (outTotal + 16 > c->h_out_cap) { if (c->h_out) cudaFreeHost(c->h_out); c->h_out = nullptr; c->h_out_cap = 0; size_t want = outTotal + outTotal / 2 + 64; CK(cudaMallocHost((void**)&c->h_out, want)); c->h_out_cap = want; }
+    CK(cudaMemcpyAsync(c->d_in.p, c->h_in, inBytes, cudaMemcpyHostToDevice, c->stream));
+    c->ctr.h2d_bytes += (int64_t)inBytes;
+
+    Params prm{};
+    prm.m = c->dm;
+    prm.gaps = c->d_gaps.p; prm.read_len = c->d_rlen.p; prm.read_off = c->d_roff.p; prm.read_mate = c->d_rmate.p;
+    prm.read_flags = c->d_rfl.p; prm.read_jlo = c->d_jlo.p; prm.read_jcut = c->d_jcut.p; prm.codes = c->d_codes.p;
+    prm.flank = c->d_flank.p; prm.pile_l = c->d_pl.p; prm.pile_r = c->d_pr.p;
+    prm.items = (const DevItem*)c->d_in.p; prm.in_arena = c->d_in.p + itemsBytes; prm.out_arena = c->d_out.p; prm.scratch = c->d_scratch.p;
+    prm.counters = c->d_ctr.p; prm.smem_bytes = smemNeed;
+
+    CK(cudaEventRecord(c->ev0, c->stream));
+    fb_em_kernel<<<n, kThreads, smemNeed, c->stream>>>(prm);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaMemcpyAsync(c->h_out, c->d_out.p, outTotal, cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long hc[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(hc, c->d_ctr.p, sizeof hc, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->ctr.device_ms += ms; c->ctr.kernel_launches += 1; c->ctr.d2h_bytes += (int64_t)outTotal;
+    c->ctr.placements_p1 = (int64_t)hc[0]; c->ctr.placements_p2 = (int64_t)hc[1]; c->ctr.base_terms = (int64_t)hc[2];
+    for (int i = 0; i < n; i++) {
+        FbItemOut* H = (FbItemOut*)(c->h_out + di[i].out_off);
+        const DevGap& g = c->hGaps[items[i].gap];
+        H->n_reads = g.n_reads; H->cand_len = items[i].cand_len; H->n_slots = di[i].n_slots;
+        H->off_p1max = di[i].off_p1; H->off_p2max = di[i].off_p2; H->off_pos2 = di[i].off_pos; H->off_soft = di[i].off_soft;
+        H->off_hard = di[i].off_hard; H->off_cov = di[i].off_cov; H->off_counts = di[i].off_counts;
+        out[i] = H;
+    }
+    return FB_OK;
+}

@@ -1,0 +1,137 @@
+"""-m gpu: the CUDA engine against the CPU oracle engine, item by item, through the C ABI.
+
+Bar (BASELINE.json north_star): discrete outputs identical (positions, consensus strings, coverage,
+round counts, flags), pass-2 products bit-exact, per-position base weights (countsGap) within 1e-5 relative.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import synth
+from figbird_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_LIB = os.path.join(ROOT, "oracle", "_build", "libfb_oracle.so")
+pytestmark = pytest.mark.gpu
+
+
+def _pair():
+    dev = capi.Engine(0)                      # raises when the CUDA library / GPU is missing: no fallback
+    assert dev.name() == "cuda-sm100a"
+    ora = capi.Engine(0, lib_path=ORACLE_LIB)
+    assert ora.name() == "oracle-cpu"
+    return dev, ora
+
+
+def _run_both(model, gaps, items):
+    dev, ora = _pair()
+    try:
+        for e in (dev, ora):
+            e.upload_model(**model)
+            e.upload_batch(gaps, None)
+        a = ora.run(items)
+        b = dev.run(items)
+    finally:
+        dev.close(); ora.close()
+    return a, b
+
+
+def _assert_same(a, b, items):
+    for i, (x, y) in enumerate(zip(a, b)):
+        bad = synth.compare_results(x, y)
+        assert not bad, "item %d %r: %s" % (i, {k: v for k, v in items[i].items() if k not in ("counts_in", "string_in")}, "; ".join(bad))
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_unmapped_em_items(seed):
+    rng = np.random.default_rng(seed)
+    model = synth.make_model(seed=seed)
+    gaps = [synth.make_gap(rng, capi.FB_MODE_UNMAPPED, 60, 55, n_reads=30),
+            synth.make_gap(rng, capi.FB_MODE_UNMAPPED, 20, 24, n_reads=25, with_n=True),
+            synth.make_gap(rng, capi.FB_MODE_UNMAPPED, 150, 140, n_reads=60, var_len=True),
+            synth.make_gap(rng, capi.FB_MODE_UNMAPPED, 8, 10, n_reads=12)]
+    items = []
+    for gi, g in enumerate(gaps):
+        for Lg in sorted({0, 1, g["true_len"] - 3, g["true_len"], g["true_len"] + 9, 3 * g["orig_len"]}):
+            if Lg < 0:
+                continue
+            items.append(dict(gap=gi, cand_len=Lg, max_rounds=200, flags=capi.FB_FLAG_EXTRA_PASS | capi.FB_FLAG_WANT_COUNTS))
+            items.append(dict(gap=gi, cand_len=Lg, max_rounds=200, flags=capi.FB_FLAG_WANT_COUNTS))
+    a, b = _run_both(model, gaps, items)
+    _assert_same(a, b, items)
+    assert any(r["calls"] > 3 for r in b)
+
+
+@pytest.mark.parametrize("seed", [4, 5])
+def test_partial_em_items(seed):
+    rng = np.random.default_rng(seed)
+    model = synth.make_model(seed=seed, partial=True)
+    gaps = [synth.make_gap(rng, capi.FB_MODE_PARTIAL, 50, 50, n_reads=40),
+            synth.make_gap(rng, capi.FB_MODE_PARTIAL, 12, 15, n_reads=20),
+            synth.make_gap(rng, capi.FB_MODE_PARTIAL, 230, 210, n_reads=80, var_len=True)]
+    items = []
+    fl = capi.FB_FLAG_RECORD_ALL | capi.FB_FLAG_NO_COMP_STOP | capi.FB_FLAG_WANT_COUNTS
+    for gi, g in enumerate(gaps):
+        for Lg in sorted({0, 2, g["true_len"] - 1, g["true_len"], g["true_len"] + 17, 300}):
+            items.append(dict(gap=gi, cand_len=Lg, max_rounds=3, flags=fl))
+    a, b = _run_both(model, gaps, items)
+    _assert_same(a, b, items)
+    assert all(r["calls"] == 3 and r["n_slots"] == 3 for r in b)
+
+
+def test_hard_items_and_resume():
+    rng = np.random.default_rng(9)
+    model = synth.make_model(seed=9)
+    gaps = [synth.make_gap(rng, capi.FB_MODE_UNMAPPED, 70, 66, n_reads=35),
+            synth.make_gap(rng, capi.FB_MODE_PARTIAL, 40, 44, n_reads=30)]
+    dev, ora = _pair()
+    try:
+        for e in (dev, ora):
+            e.upload_model(**model); e.upload_batch(gaps, None)
+        # one round, then resume from the returned counts (the host-driven large-gap path)
+        first = [dict(gap=0, cand_len=70, max_rounds=1, flags=capi.FB_FLAG_WANT_COUNTS)]
+        a0, b0 = ora.run(first), dev.run(first)
+        _assert_same(a0, b0, first)
+        nxt = [dict(gap=0, cand_len=70, max_rounds=1, flags=capi.FB_FLAG_WANT_COUNTS | capi.FB_FLAG_RESUME, comp_count_in=a0[0]["comp_count"],
+                    counts_in=a0[0]["counts"], string_in=a0[0]["hard"])]
+        a1, b1 = ora.run(nxt), dev.run(nxt)
+        _assert_same(a1, b1, nxt)
+        # two single rounds == one two-round item
+        two = [dict(gap=0, cand_len=70, max_rounds=2, flags=capi.FB_FLAG_WANT_COUNTS | capi.FB_FLAG_NO_COMP_STOP)]
+        b2 = dev.run(two)
+        assert np.array_equal(b2[0]["hard"], b1[0]["hard"]) and np.array_equal(b2[0]["pos2"], b1[0]["pos2"])
+        # hard placement on a given string, both finalize semantics
+        hard = [dict(kind=capi.FB_ITEM_HARD, gap=0, cand_len=70, string_in=a1[0]["soft"]),
+                dict(kind=capi.FB_ITEM_HARD, gap=1, cand_len=40, string_in=rng.integers(0, 5, 40).astype(np.uint8), flags=capi.FB_FLAG_FINALIZE_REF),
+                dict(kind=capi.FB_ITEM_HARD, gap=1, cand_len=52, string_in=rng.integers(0, 4, 52).astype(np.uint8))]
+        a3, b3 = ora.run(hard), dev.run(hard)
+        _assert_same(a3, b3, hard)
+    finally:
+        dev.close(); ora.close()
+
+
+def test_large_candidate_uses_global_tables():
+    """Lg large enough that the row tables no longer fit in shared memory."""
+    rng = np.random.default_rng(11)
+    model = synth.make_model(seed=11)
+    gaps = [synth.make_gap(rng, capi.FB_MODE_UNMAPPED, 1500, 1400, n_reads=120)]
+    items = [dict(gap=0, cand_len=1500, max_rounds=2, flags=capi.FB_FLAG_WANT_COUNTS | capi.FB_FLAG_NO_COMP_STOP),
+             dict(gap=0, cand_len=2600, max_rounds=1, flags=capi.FB_FLAG_WANT_COUNTS)]
+    a, b = _run_both(model, gaps, items)
+    _assert_same(a, b, items)
+
+
+def test_deterministic_across_runs():
+    rng = np.random.default_rng(12)
+    model = synth.make_model(seed=12)
+    gaps = [synth.make_gap(rng, capi.FB_MODE_UNMAPPED, 90, 80, n_reads=50)]
+    items = [dict(gap=0, cand_len=L, max_rounds=200, flags=capi.FB_FLAG_EXTRA_PASS | capi.FB_FLAG_WANT_COUNTS) for L in (80, 90, 100)]
+    dev = capi.Engine(0)
+    try:
+        dev.upload_model(**model); dev.upload_batch(gaps, None)
+        r1 = dev.run(items); r2 = dev.run(list(reversed(items)))
+    finally:
+        dev.close()
+    for x, y in zip(r1, reversed(r2)):
+        assert np.array_equal(x["counts"], y["counts"]) and np.array_equal(x["p1max"], y["p1max"])
