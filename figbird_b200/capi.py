@@ -55,7 +55,7 @@ class FbCounters(C.Structure):
 
 
 EXPORTS = ["fb_ctx_create", "fb_ctx_destroy", "fb_last_error", "fb_engine_name", "fb_model_upload", "fb_batch_upload", "fb_em_run",
-           "fb_get_counters", "fb_fillgaps_main"]
+           "fb_get_counters", "fb_microbench_fp64", "fb_fillgaps_main"]
 
 
 def load(lib_path=None):
@@ -72,6 +72,7 @@ def load(lib_path=None):
     lib.fb_batch_upload.argtypes = [C.c_void_p, C.POINTER(FbGapBatch)]; lib.fb_batch_upload.restype = C.c_int32
     lib.fb_em_run.argtypes = [C.c_void_p, C.POINTER(FbWorkItem), C.c_int32, C.POINTER(C.POINTER(FbItemOut))]; lib.fb_em_run.restype = C.c_int32
     lib.fb_get_counters.argtypes = [C.c_void_p, C.POINTER(FbCounters)]; lib.fb_get_counters.restype = C.c_int32
+    lib.fb_microbench_fp64.argtypes = [C.c_void_p, C.POINTER(C.c_double)]; lib.fb_microbench_fp64.restype = C.c_int32
     lib.fb_fillgaps_main.argtypes = [C.c_int32, C.POINTER(C.c_char_p)]; lib.fb_fillgaps_main.restype = C.c_int32
     return lib
 
@@ -185,6 +186,11 @@ class Engine:
                      cov=arr(H.off_cov, np.int32, Lg), counts=arr(H.off_counts, np.float64, 5 * Lg).reshape(Lg, 5) if H.off_counts >= 0 else None)
             res.append(r)
         return res
+
+    def microbench_fp64(self):
+        out = (C.c_double * 2)()
+        self._check(self.lib.fb_microbench_fp64(self.h, out), "fb_microbench_fp64")
+        return {"dmul_tinstr_s": out[0], "dfma_tflops": out[1]}
 
     def counters(self):
         c = FbCounters()

@@ -428,6 +428,18 @@ __global__ void __launch_bounds__(kThreads) fb_em_kernel(const Params prm) {
     }
 }
 
+// ---- diagnostic: FP64 pipe peak without FMA contraction (the ceiling of this path) and with FMA
+template <int MODE>
+__global__ void __launch_bounds__(256) fb_fp64_peak_kernel(double* out, int iters) {
+    double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3, a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+    const double m = 0.9999999, b = 1e-12;
+    for (int i = 0; i < iters; i++) {
+        if (MODE == 0) { a0 = __dmul_rn(a0, m); a1 = __dmul_rn(a1, m); a2 = __dmul_rn(a2, m); a3 = __dmul_rn(a3, m); a4 = __dmul_rn(a4, m); a5 = __dmul_rn(a5, m); a6 = __dmul_rn(a6, m); a7 = __dmul_rn(a7, m); }
+        else { a0 = __fma_rn(a0, m, b); a1 = __fma_rn(a1, m, b); a2 = __fma_rn(a2, m, b); a3 = __fma_rn(a3, m, b); a4 = __fma_rn(a4, m, b); a5 = __fma_rn(a5, m, b); a6 = __fma_rn(a6, m, b); a7 = __fma_rn(a7, m, b); }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { c->err = std::string(#x) + ": " + cudaGetErrorString(e_); return FB_ERR_CUDA; } } while (0)
 
 template <class T> struct DevBuf {
@@ -677,5 +689,32 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
         H->off_hard = di[i].off_hard; H->off_cov = di[i].off_cov; H->off_counts = di[i].off_counts;
         out[i] = H;
     }
+    return FB_OK;
+}
+
+// Diagnostic (bench.py roofline denominator): measured FP64 instruction throughput of this GPU.
+// out[0] = DMUL-only rate in 1e12 instructions/s (1 flop each: the no-FMA ceiling this path lives under),
+// out[1] = DFMA rate in TFLOP/s (2 flop each).
+extern "C" fb_status fb_microbench_fp64(fb_ctx* c, double* out2) {
+    if (!c || !out2) return FB_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, c->device));
+    const int blocks = pr.multiProcessorCount * 8, iters = 1 << 14;
+    DevBuf<double> buf; CK(buf.ensure((size_t)blocks * 256));
+    for (int mode = 0; mode < 2; mode++) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 5; rep++) {
+            CK(cudaEventRecord(c->ev0, c->stream));
+            if (mode == 0) fb_fp64_peak_kernel<0><<<blocks, 256, 0, c->stream>>>(buf.p, iters); else fb_fp64_peak_kernel<1><<<blocks, 256, 0, c->stream>>>(buf.p, iters);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(c->ev1, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        const double ops = (double)blocks * 256 * 8 * (double)iters;
+        out2[mode] = ops * (mode == 0 ? 1.0 : 2.0) / (best * 1e-3) / 1e12;
+    }
+    buf.release();
     return FB_OK;
 }

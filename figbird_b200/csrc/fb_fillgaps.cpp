@@ -127,7 +127,8 @@ int fillgapsMain(int argc, const char* const* argv) {
     auto t0 = clk::now();
     std::vector<GapRecord> gaps; int totGaps = 0;
     if (!loadGapRecords(a.tmpDir, gaps, totGaps)) { fprintf(stderr, "Couldn't open gapinfo in Fillgaps.cpp\n"); return 1; }
-    printf("Total # of gaps = %d\n", totGaps);
+    const bool quiet = getenv("FIGBIRD_QUIET") != nullptr;
+    if (!quiet) printf("Total # of gaps = %d\n", totGaps);
     Scaffolds sc;
     if (!loadScaffolds(a.draft, sc)) { printf("Can't open contig file\n"); return 1; }
     auto t1 = clk::now();
@@ -259,8 +260,8 @@ int fillgapsMain(int argc, const char* const* argv) {
             fclose(mf);
         }
     }
-    printf("Time taken = %d seconds\n", (int)secs(t0, t5));
-    printf("======================================\nIteration %d ends successfully\n======================================\n", a.scriptItr);
+    if (!quiet) printf("Time taken = %d seconds\n", (int)secs(t0, t5));
+    if (!quiet) printf("======================================\nIteration %d ends successfully\n======================================\n", a.scriptItr);
     return 0;
 }
 

@@ -173,6 +173,11 @@ fb_status fb_em_run(fb_ctx* ctx, const FbWorkItem* items, int32_t n_items, const
 
 fb_status fb_get_counters(const fb_ctx* ctx, FbCounters* out);
 
+/* Diagnostic for the roofline report: measured FP64 throughput of the device.  out2[0] = DMUL-only rate
+ * (1e12 instr/s == TFLOP/s at 1 flop per instruction, the ceiling when FMA contraction is forbidden),
+ * out2[1] = DFMA rate in TFLOP/s (2 flop per instruction). */
+fb_status fb_microbench_fp64(fb_ctx* ctx, double* out2);
+
 /* Level 1: the FillGaps executable as a function.  argv[1..15] as FillGaps.cpp:419-433.  Returns the
  * process exit status the reference would give (0 ok, 1 on unreadable inputs).  GPUs: devices listed in
  * FIGBIRD_GPUS (default: device 0); gaps are sharded cost-balanced across them. */

@@ -1,0 +1,90 @@
+"""-m gpu: the product (`fillgaps` / fb_fillgaps_main on the CUDA engine) against the reference's golden
+outputs, plus size-independent properties at larger sizes."""
+import os
+import re
+
+import pytest
+
+import fbcase as fc
+import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", params=gu.NAMES)
+def case(request, tmp_path_factory):
+    d = tmp_path_factory.mktemp("golden_gpu_" + request.param)
+    return gu.extract(request.param, str(d))
+
+
+@pytest.mark.parametrize("mode", ["partial", "unmapped"])
+def test_product_matches_reference_golden(case, mode):
+    o = fc.run_ours(case, mode, fc.product_exe(), extra_env={"FIGBIRD_METRICS": os.path.join(case, "m_%s.json" % mode)})
+    exp = gu.expected(case, mode)
+    for f in ("gapout.txt", "filledContigs.fa", "Ncount.txt", "draw.txt"):
+        assert o[f] == exp[f], "%s differs from the reference (%s mode)" % (f, mode)
+    assert '"engine": "cuda-sm100a"' in open(os.path.join(case, "m_%s.json" % mode)).read()
+
+
+def test_in_process_entry_point(case):
+    from figbird_b200 import capi
+    run = os.path.join(case, "run_inproc")
+    os.makedirs(os.path.join(run, "Temp"), exist_ok=True)
+    import shutil
+    for f in ("gapInfo.txt", "stat.txt", "stat2.txt"):
+        shutil.copy(os.path.join(case, "unmapped", "Temp", f), os.path.join(run, "Temp", f))
+    rc = capi.fillgaps(fc.fillgaps_argv(case, "unmapped", os.path.join(run, "Temp")))
+    assert rc == 0
+    exp = gu.expected(case, "unmapped")
+    assert open(os.path.join(run, "Temp", "gapout.txt"), "rb").read() == exp["gapout.txt"]
+
+
+def test_missing_inputs_exit_1(tmp_path):
+    from figbird_b200 import capi
+    argv = [str(tmp_path / "nope.fa"), "200", "100", "1", "1", "0", "1", str(tmp_path / "myout.sam"), str(tmp_path) + "/", str(tmp_path) + "/", "30", "100", "0", "0", "200"]
+    assert capi.fillgaps(argv) == 1
+
+
+@pytest.fixture(scope="module")
+def big_case(tmp_path_factory):
+    if not fc.have_reference():
+        pytest.skip("oracle/_ref (reference Preprocess) not available to prepare inputs")
+    d = tmp_path_factory.mktemp("big")
+    return fc.make_case(str(d / "c1"), {"genome": 1000000, "scaffolds": 4, "gaps": 50, "gapmin": 10, "gapmax": 500, "cov": 30, "sd": 20, "seed": 101, "near": 700, "model-pairs": 100000})
+
+
+@pytest.mark.parametrize("mode", ["partial", "unmapped"])
+def test_properties_at_c1_size(big_case, mode):
+    """BASELINE configs[0] size: determinism, invariance to sharding / batching, and output self-consistency."""
+    a = fc.run_ours(big_case, mode, fc.product_exe(), name="a")
+    b = fc.run_ours(big_case, mode, fc.product_exe(), extra_env={"FIGBIRD_GPUS": "0,0", "FIGBIRD_INFLIGHT": "7"}, name="b")
+    for f in ("gapout.txt", "filledContigs.fa", "Ncount.txt", "draw.txt"):
+        assert a[f] == b[f], f
+    # self-consistency of the three files
+    draft = open(os.path.join(big_case, "draft.fa")).read().split("\n")
+    dlen = sum(len(l) for l in draft if l and not l.startswith(">"))
+    delta, n_left = 0, 0
+    for line in a["gapout.txt"].decode().split("\n"):
+        if not line:
+            continue
+        t = line.split("\t")
+        og, sl, s = int(t[3]), int(t[4]), t[5] if len(t) > 5 else ""
+        assert sl == len(s) and re.fullmatch(r"[ACGTN]*", s)
+        delta += sl - og
+        n_left += s.count("N")
+    filled = a["filledContigs.fa"].decode().split("\n")
+    flen = sum(len(l) for l in filled if l and not l.startswith(">"))
+    assert flen == dlen + delta
+    assert a["Ncount.txt"] == (b"0" if n_left == 0 else b"1")
+    # most gaps of this synthetic draft get closed or shortened
+    assert sum(1 for l in a["gapout.txt"].decode().split("\n") if l and "N" not in l.split("\t")[5]) >= 10
+
+
+def test_c1_against_live_reference(big_case):
+    """Full BASELINE configs[0] differential check (reference runs with numthreads=4 as the config says)."""
+    if os.environ.get("FB_SKIP_LIVE_REF"):
+        pytest.skip("disabled")
+    r = fc.run_reference(big_case, "partial", threads=4)
+    o = fc.run_ours(big_case, "partial", fc.product_exe(), name="live")
+    for f in ("gapout.txt", "filledContigs.fa", "Ncount.txt"):
+        assert r[f] == o[f], f
