@@ -142,9 +142,8 @@ __global__ void __launch_bounds__(kThreads) fb_em_kernel(const Params prm) {
 
     // ---- gapString flanks
     for (int r = tid; r < rows; r += kThreads) {
-        unsigned char c = 4;
-        if (r < F) c = lf[r]; else if (r >= F + Lg) c = rf[r - F - Lg];
-        G[r] = c;
+        if (r >= F && r < F + Lg) continue;          // gap rows are written by the consensus / string_in (other threads)
+        G[r] = (r < F) ? lf[r] : rf[r - F - Lg];
     }
     int prevValid = 0;   // previous hard consensus present (uniform)
 
@@ -332,7 +331,14 @@ __global__ void __launch_bounds__(kThreads) fb_em_kernel(const Params prm) {
                         }
                         if (p > 0.0) {
                             if (unm) { const double s = log10(p); w = exp(0.5 * s); }     // Figbird.cpp:3591,3601
-                            else { const double s = log(p); w = pow(10.0, s); }           // Figbird.cpp:3169,3179
+                            else {
+                                // Figbird.cpp:3169,3179: w = pow(10, ln p).  These weights run down into the subnormal range and
+                                // the reference's consensus still sees them (a row whose only vote is 4.9e-324 gets that base),
+                                // so gradual underflow must round like glibc's pow: evaluate 300 decades higher (exact shift of
+                                // the exponent argument) and let one IEEE multiply do the final, correctly rounded, scaling.
+                                const double s = log(p);
+                                w = (s < -290.0) ? __dmul_rn(pow(10.0, s + 300.0), 1e-300) : pow(10.0, s);
+                            }
                         } else p = 0.0;
                     }
                     // per-read maximum of the raw product (positive doubles order like their bit patterns)
@@ -370,7 +376,7 @@ __global__ void __launch_bounds__(kThreads) fb_em_kernel(const Params prm) {
                 __syncthreads();
             }
             // pass-1 maxima: bit pattern 0 means no admissible offset -> -1
-            for (int q = tid; q < R; q += kThreads) { double v = oP1[(size_t)slot * R + q]; if (!(v > 0.0)) oP1[(size_t)slot * R + q] = -1.0; }
+            for (int q = tid; q < R; q += kThreads) { double v = __ldcg(&oP1[(size_t)slot * R + q]); if (!(v > 0.0)) oP1[(size_t)slot * R + q] = -1.0; }   // atomics live in L2: bypass L1
             // ================= computeSequence(0,0) =================
             for (int x = tid; x < Lg; x += kThreads) {
                 double mx = 0; int mi = -1;
@@ -390,7 +396,7 @@ __global__ void __launch_bounds__(kThreads) fb_em_kernel(const Params prm) {
                 for (int x = tid; x < Lg; x += kThreads) {
                     int mx = 0, mi = -1;
 #pragma unroll
-                    for (int k = 0; k < 5; k++) { int v = NC[(size_t)k * Lg + x]; if (v > mx) { mx = v; mi = k; } }
+                    for (int k = 0; k < 5; k++) { int v = it.tables_in_smem ? NC[(size_t)k * Lg + x] : __ldcg(&NC[(size_t)k * Lg + x]); if (v > mx) { mx = v; mi = k; } }
                     unsigned char h = (mx > 0 && mi >= 0 && mi < 4) ? (unsigned char)mi : 4;
                     oHard[x] = h; oCov[x] = mx;
                     if (!prevValid || PREV[x] != h) same = 0;

@@ -171,6 +171,13 @@ int fillgapsMain(int argc, const char* const* argv) {
         for (int g : order) { int d = (int)(std::min_element(load.begin(), load.end()) - load.begin()); shard[d].push_back(g); load[d] += fills[g]->prepared().cost + 1; }
     }
     std::vector<GapResult> results(nG);
+    std::vector<char> onlyGap(nG, 1);
+    if (const char* og = getenv("FIGBIRD_ONLY_GAPS")) {   // debugging aid: fill only the listed gaps, leave the rest as N
+        std::fill(onlyGap.begin(), onlyGap.end(), 0);
+        for (const char* q = og; *q;) { int v = atoi(q); if (v >= 0 && v < nG) onlyGap[v] = 1; while (*q && *q != ',') q++; if (*q) q++; }
+        for (int g = 0; g < nG; g++) if (!onlyGap[g]) { results[g].gapStringLength = gaps[g].gapLength; results[g].gapString.assign(gaps[g].gapLength, 'N'); }
+        for (auto& sh : shard) { std::vector<int> keep; for (int g : sh) if (onlyGap[g]) keep.push_back(g); sh.swap(keep); }
+    }
     std::vector<std::string> devErr(nD);
     std::vector<FbCounters> devCtr(nD); std::vector<int64_t> devTicks(nD, 0);
     std::vector<std::thread> devThreads;
