@@ -135,3 +135,27 @@ def test_deterministic_across_runs():
         dev.close()
     for x, y in zip(r1, reversed(r2)):
         assert np.array_equal(x["counts"], y["counts"]) and np.array_equal(x["p1max"], y["p1max"])
+
+
+def test_partial_subnormal_weights():
+    """Partial-mode weights pow(10, ln p) underflow gradually; rows whose only votes are subnormal still decide the
+    reference's consensus, so the device must round them like glibc (regression: found at C2 scale by the dual engine)."""
+    rng = np.random.default_rng(21)
+    model = synth.make_model(seed=21, partial=True)
+    gaps = []
+    for _ in range(6):
+        g = synth.make_gap(rng, capi.FB_MODE_PARTIAL, 180, 170, n_reads=40)
+        # make half of the reads unrelated to the locus: their products fall to 1e-130..1e-160, weights to ~1e-320
+        for r in g["reads"][::2]:
+            r["codes"] = rng.integers(0, 4, len(r["codes"])).astype(np.uint8)
+        gaps.append(g)
+    fl = capi.FB_FLAG_RECORD_ALL | capi.FB_FLAG_NO_COMP_STOP | capi.FB_FLAG_WANT_COUNTS
+    items = [dict(gap=gi, cand_len=Lg, max_rounds=3, flags=fl) for gi in range(len(gaps)) for Lg in (120, 150, 170, 180, 200, 260)]
+    a, b = _run_both(model, gaps, items)
+    sub = sum(int(((r["counts"] > 0) & (r["counts"] < 2.3e-308)).sum()) for r in a)
+    assert sub > 0, "test does not reach the subnormal range"
+    for i, (x, y) in enumerate(zip(a, b)):
+        assert np.array_equal(x["soft"], y["soft"]), "item %d soft consensus" % i
+        assert np.array_equal(x["pos2"][:3], y["pos2"][:3]) and np.array_equal(x["p2max"][:3], y["p2max"][:3])
+        m = (x["counts"] > 0) & (x["counts"] < 2.3e-308)
+        assert np.array_equal(x["counts"][m], y["counts"][m]), "subnormal weights must match bit for bit"

@@ -88,3 +88,22 @@ def test_c1_against_live_reference(big_case):
     o = fc.run_ours(big_case, "partial", fc.product_exe(), name="live")
     for f in ("gapout.txt", "filledContigs.fa", "Ncount.txt"):
         assert r[f] == o[f], f
+
+
+def test_c2_full_size_against_reference_golden(tmp_path_factory):
+    """BASELINE configs[1] at full size (500 gaps): gapout.txt of both modes byte-identical to what the reference
+    FillGaps + Figbird (-O2 worker, 8 threads) wrote for the same seeded inputs (tests/golden/c2_*.gz, produced
+    by running oracle/_ref in the dev container; inputs are regenerated here from the same seed)."""
+    if not fc.have_reference():
+        pytest.skip("oracle/_ref (reference Preprocess) not available to prepare inputs")
+    import gzip
+    import hashlib
+    import bench
+    d = tmp_path_factory.mktemp("c2")
+    case = bench.prepare_case(str(d / "c2"), bench.WORKLOADS["c2"], 102)
+    md5s = open(os.path.join(gu.GOLDEN, "c2_filled.md5")).read().split()
+    for i, mode in enumerate(("partial", "unmapped")):
+        o = fc.run_ours(case, mode, fc.product_exe(), threads=8)
+        exp = gzip.open(os.path.join(gu.GOLDEN, "c2_gapout_%s.txt.gz" % mode)).read()
+        assert o["gapout.txt"] == exp, "c2 %s gapout differs from the reference" % mode
+        assert hashlib.md5(o["filledContigs.fa"]).hexdigest() == md5s[i]
