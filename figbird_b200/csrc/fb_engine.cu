@@ -22,6 +22,7 @@
 // doubles.  There is no CPU path in this file: without a device fb_ctx_create fails.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
@@ -36,7 +37,9 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxSmem = 200 * 1024;      // dynamic shared memory we opt in to (227 KB is the sm_100 limit)
-constexpr int kMinW = 16 * 1024;          // least W-buffer bytes we accept before moving tables to global
+constexpr int kChunkWant = 40 * 1024;     // W + read-code staging we ask for per CTA when the reads allow it
+constexpr int kNumBuckets = 4;
+__host__ __device__ constexpr int bucketCap(int b) { return b == 0 ? 28 * 1024 : b == 1 ? 56 * 1024 : b == 2 ? 100 * 1024 : kMaxSmem; }
 
 struct DevGap { long long gap_start; int mode, orig_len, n_reads, read_begin, flank_len, flank_begin, pile_len, pile_begin; };
 
@@ -50,7 +53,7 @@ struct DevItem {
 };
 
 struct DevModel {
-    const double* e; const double* ome; const double* match; const double* mism;   // [k], [k], [k], [k][25]
+    const double* e; const double* ome; const double* match;   // [k]
     const double* pdf; int n_insert;
     double etp[25];
     int tmin, tmax, max_read_len;
@@ -66,8 +69,40 @@ struct Params {
     const DevItem* items;
     const unsigned char* in_arena; unsigned char* out_arena; unsigned char* scratch;
     unsigned long long* counters;   // [0] pass-1 placements, [1] pass-2 placements, [2] base terms
-    int smem_bytes;
 };
+
+// Shared-memory plan of one item, computed identically on host (sizing, bucketing) and device (carving).
+//   table region (shared memory, or a global scratch slice for very long candidates):
+//     UT[5][S] double2 {P,E}: slot f<5 = flank row of scaffold code f, slot 5+x = gap row x   (S = 5+Lg)
+//     C[5][Lg] countsGap, GP[split][5][Lg] gather partials, NC[5][Lg] new_counts_gap, RS[rows] slot of window row,
+//     G[rows] gapString codes, PREV[Lg] previous hard consensus
+//   local region (always shared): MT1[k]={1-e,e}, MT2[k]={1-e-ins-del,e}, ETP[25], then per chunk of reads RC (codes) and W.
+struct Plan { int S, rows, split, oUT, oC, oGP, oNC, oRS, oG, oPREV, tableBytes, oMT1, oMT2, oETP, localFixed, maxLenPad, strideP, perRead; };
+__host__ __device__ inline int al16(int x) { return (x + 15) & ~15; }
+__host__ __device__ inline Plan makePlan(int Lg, int F, int modelLen, int maxLen, int mode) {
+    Plan p;
+    p.S = 5 + Lg; p.rows = Lg + 2 * F;
+    p.split = (Lg >= 128 || Lg <= 0) ? 1 : (kThreads / Lg > 8 ? 8 : kThreads / Lg);
+    int o = 0;
+    p.oUT = o; o += 16 * 5 * p.S;
+    p.oC = o; o += 8 * 5 * Lg;
+    p.oGP = o; o += (p.split > 1) ? 8 * 5 * Lg * p.split : 0;
+    p.oNC = o; o += 4 * 5 * Lg;
+    p.oRS = o; o += al16(2 * p.rows);
+    p.oG = o; o += al16(p.rows);
+    p.oPREV = o; o += al16(Lg);
+    p.tableBytes = al16(o);
+    o = 0;
+    p.oMT1 = o; o += 16 * modelLen;
+    p.oMT2 = o; o += 16 * modelLen;
+    p.oETP = o; o += 208;
+    p.localFixed = al16(o);
+    p.maxLenPad = (maxLen + 15) & ~15;
+    const int stride = (mode == FB_MODE_UNMAPPED) ? (maxLen + Lg - 1) : (maxLen - 1);
+    p.strideP = stride > 1 ? stride : 1;
+    p.perRead = 8 * p.strideP + p.maxLenPad;
+    return p;
+}
 
 __device__ __forceinline__ bool admissible(const DevModel& m, const DevGap& g, int fl, int rel, int len, int x0, int Lg, bool finalizeRef, int* tOut) {
     const long long off = (long long)Lg - g.orig_len;
@@ -103,28 +138,50 @@ __device__ __forceinline__ void errRow(const double* etp, const double p[4], dou
     }
 }
 
-__global__ void __launch_bounds__(kThreads) fb_em_kernel(const Params prm) {
-    const DevItem it = prm.items[blockIdx.x];
+// soft weight of one placement (Figbird.cpp:3591,3601 unmapped; :3169,3179 partial)
+__device__ __forceinline__ double placementWeight(double p, bool unm) {
+    if (unm) { const double s = log10(p); return exp(0.5 * s); }
+    // partial: w = pow(10, ln p).  These weights run down into the subnormal range and the reference's consensus still
+    // sees them (a row whose only vote is 4.9e-324 gets that base), so gradual underflow must round like glibc's pow:
+    // evaluate 300 decades higher (exact shift of the exponent argument) and let one IEEE multiply do the final scaling.
+    const double s = log(p);
+    return (s < -290.0) ? __dmul_rn(pow(10.0, s + 300.0), 1e-300) : pow(10.0, s);
+}
+
+template <bool TSMEM>
+__global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Params prm, const int* __restrict__ order, const int smemBytes) {
+    const DevItem it = prm.items[order[blockIdx.x]];
     const DevGap g = prm.gaps[it.gap];
     const DevModel& m = prm.m;
-    const int Lg = it.Lg, F = g.flank_len, rows = Lg + 2 * F, R = g.n_reads;
+    const int Lg = it.Lg, F = g.flank_len, R = g.n_reads;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const Plan pl = makePlan(Lg, F, m.max_read_len, it.max_len, g.mode);
+    const int S = pl.S, rows = pl.rows;
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_comp, s_same, s_stop, s_flags;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_comp, s_same, s_flags;
     __shared__ unsigned long long s_place1, s_place2, s_terms;
 
-    // ---- carve the row tables (shared memory, or this item's global scratch when they do not fit)
-    unsigned char* tb = it.tables_in_smem ? smem_raw : (prm.scratch + it.scratch_off);
-    double* P = (double*)tb;                 // [4][rows]
-    double* E = P + 4 * (size_t)rows;        // [5][rows]
-    double* C = E + 5 * (size_t)rows;        // [5][Lg]   countsGap gap rows
-    int* NC = (int*)(C + 5 * (size_t)Lg);    // [5][Lg]   new_counts_gap gap rows
-    unsigned char* G = (unsigned char*)(NC + 5 * (size_t)Lg);   // [rows] gapString codes
-    unsigned char* PREV = G + rows;          // [Lg] previous hard consensus
-    size_t tbBytes = ((size_t)(PREV + Lg - tb) + 15) & ~(size_t)15;
-    double* W = (double*)(it.tables_in_smem ? smem_raw + tbBytes : smem_raw);
-    const int wCap = (int)((prm.smem_bytes - (it.tables_in_smem ? tbBytes : 0)) / sizeof(double));
+    unsigned char* const tbase = TSMEM ? smem : (prm.scratch + it.scratch_off);
+    unsigned char* const lbase = TSMEM ? smem + pl.tableBytes : smem;
+    double2* const UT = (double2*)(tbase + pl.oUT);
+    double* const C = (double*)(tbase + pl.oC);
+    double* const GP = (double*)(tbase + pl.oGP);
+    int* const NC = (int*)(tbase + pl.oNC);
+    unsigned short* const RS = (unsigned short*)(tbase + pl.oRS);
+    unsigned char* const G = tbase + pl.oG;
+    unsigned char* const PREV = tbase + pl.oPREV;
+    double2* const MT1 = (double2*)(lbase + pl.oMT1);
+    double2* const MT2 = (double2*)(lbase + pl.oMT2);
+    double* const ETP = (double*)(lbase + pl.oETP);
+    unsigned char* const chunkBase = lbase + pl.localFixed;
+    const int chunkBytes = smemBytes - (TSMEM ? pl.tableBytes : 0) - pl.localFixed;
+    const int chunkReads = max(1, min(R > 0 ? R : 1, chunkBytes / pl.perRead));
+    unsigned char* const RC = chunkBase;                                    // [chunkReads][maxLenPad]
+    double* const W = (double*)(chunkBase + al16(chunkReads * pl.maxLenPad));   // [chunkReads][strideP]
+    const int strideP = pl.strideP, mlp = pl.maxLenPad;
+    const int cpr = (strideP + 63) / 64;     // 64-offset units per read (two offsets per lane)
+    const bool singleChunk = chunkReads >= R;
 
     unsigned char* out = prm.out_arena + it.out_off;
     double* oP1 = (double*)(out + it.off_p1);
@@ -138,54 +195,54 @@ __global__ void __launch_bounds__(kThreads) fb_em_kernel(const Params prm) {
     const unsigned char* rf = lf + F;
     const bool unm = (g.mode == FB_MODE_UNMAPPED);
 
-    if (tid == 0) { s_comp = 0; s_stop = 0; s_flags = 0; s_place1 = 0; s_place2 = 0; s_terms = 0; }
-
-    // ---- gapString flanks
+    if (tid == 0) { s_comp = 0; s_flags = 0; s_place1 = 0; s_place2 = 0; s_terms = 0; }
+    // ---- model tables and window maps
+    for (int k = tid; k < m.max_read_len; k += kThreads) { MT1[k] = make_double2(m.ome[k], m.e[k]); MT2[k] = make_double2(m.match[k], m.e[k]); }
+    if (tid < 25) ETP[tid] = m.etp[tid];
     for (int r = tid; r < rows; r += kThreads) {
-        if (r >= F && r < F + Lg) continue;          // gap rows are written by the consensus / string_in (other threads)
-        G[r] = (r < F) ? lf[r] : rf[r - F - Lg];
+        const int x = r - F;
+        if (x >= 0 && x < Lg) RS[r] = (unsigned short)(5 + x);     // gap row (G[r] is written by the consensus / string_in)
+        else { const unsigned char c = (r < F) ? lf[r] : rf[r - F - Lg]; RS[r] = c; G[r] = c; }
     }
     int prevValid = 0;   // previous hard consensus present (uniform)
 
+    auto storeRow = [&](int slot, const double p[4], const double e[5]) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) UT[k * S + slot] = make_double2(p[k], e[k]);
+        UT[4 * S + slot] = make_double2(0.0, e[4]);     // read base N: term = e*E[4] == 0*(1-e) + e*E[4] exactly
+    };
+
     if (it.kind == FB_ITEM_EM) {
-        // flank rows: one-hot counts -> P, E (initialize + computeProbsGap, Figbird.cpp:2342-2372, 2090-2109)
-        for (int r = tid; r < rows; r += kThreads) {
-            if (r >= F && r < F + Lg) continue;
-            const int f = (r < F) ? lf[r] : rf[r - F - Lg];
+        // the five kinds of flank rows: one-hot counts (or 1 on N) -> P, E (initialize + computeProbsGap, Figbird.cpp:2342-2372, 2090-2109)
+        if (tid < 5) {
             double p[4], e[5];
 #pragma unroll
-            for (int k = 0; k < 4; k++) p[k] = (f == 4) ? 0.25 : (f == k ? 1.0 : 0.0);
+            for (int k = 0; k < 4; k++) p[k] = (tid == 4) ? 0.25 : (tid == k ? 1.0 : 0.0);
             errRow(m.etp, p, e);
-#pragma unroll
-            for (int k = 0; k < 4; k++) P[(size_t)k * rows + r] = p[k];
-#pragma unroll
-            for (int k = 0; k < 5; k++) E[(size_t)k * rows + r] = e[k];
+            storeRow(tid, p, e);
         }
         if (it.flags & FB_FLAG_RESUME) {
             const double* cin = (const double*)(prm.in_arena + it.counts_in_off);
-            for (int i = tid; i < 5 * Lg; i += kThreads) { int x = i / 5, k = i % 5; C[(size_t)k * Lg + x] = cin[i]; }
+            for (int i = tid; i < 5 * Lg; i += kThreads) { int x = i / 5, k = i % 5; C[k * Lg + x] = cin[i]; }
             if (it.string_in_off >= 0) { const unsigned char* sin = prm.in_arena + it.string_in_off; for (int x = tid; x < Lg; x += kThreads) PREV[x] = sin[x]; prevValid = 1; }
             if (tid == 0) s_comp = it.comp_in;
         } else {
             // gap rows from the partial pile-ups (update_partial_prob, Figbird.cpp:2039-2081)
-            const int* pl = prm.pile_l + 4 * (size_t)g.pile_begin; const int* pr = prm.pile_r + 4 * (size_t)g.pile_begin;
+            const int* plp = prm.pile_l + 4 * (size_t)g.pile_begin; const int* prp = prm.pile_r + 4 * (size_t)g.pile_begin;
             for (int x = tid; x < Lg; x += kThreads) {
                 double cnt[4]; int tot = 0;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     int c = 1;
-                    if (x < g.pile_len) c += pl[4 * x + k];
-                    int u = Lg - 1 - x; if (u < g.pile_len) c += pr[4 * u + k];
+                    if (x < g.pile_len) c += plp[4 * x + k];
+                    int u = Lg - 1 - x; if (u < g.pile_len) c += prp[4 * u + k];
                     cnt[k] = (double)c; tot += c;
                 }
                 double p[4], e[5];
 #pragma unroll
                 for (int k = 0; k < 4; k++) p[k] = __ddiv_rn(cnt[k], (double)tot);
                 errRow(m.etp, p, e);
-#pragma unroll
-                for (int k = 0; k < 4; k++) P[(size_t)k * rows + F + x] = p[k];
-#pragma unroll
-                for (int k = 0; k < 5; k++) E[(size_t)k * rows + F + x] = e[k];
+                storeRow(5 + x, p, e);
             }
         }
     } else {
@@ -193,6 +250,16 @@ __global__ void __launch_bounds__(kThreads) fb_em_kernel(const Params prm) {
         for (int x = tid; x < Lg; x += kThreads) { unsigned char c = it.string_in_off >= 0 ? sin[x] : 4; G[F + x] = c; oSoft[x] = c; oHard[x] = 4; oCov[x] = 0; }
         for (int q = tid; q < R; q += kThreads) oP1[q] = -1.0;
     }
+
+    auto stageReads = [&](int q0, int q1) {   // read codes of the chunk -> RC
+        const int n = (q1 - q0) * mlp;
+        for (int i = tid; i < n; i += kThreads) {
+            const int ql = i / mlp, j = i - ql * mlp;
+            const int qi = g.read_begin + q0 + ql;
+            RC[i] = (j < prm.read_len[qi]) ? prm.codes[prm.read_off[qi] + j] : (unsigned char)4;
+        }
+    };
+    if (singleChunk) stageReads(0, R);
     __syncthreads();
 
     // M-step over the gap rows (flank rows never change): computeProbsGap(0) + computeErrorProbsGap
@@ -200,7 +267,7 @@ __global__ void __launch_bounds__(kThreads) fb_em_kernel(const Params prm) {
         for (int x = tid; x < Lg; x += kThreads) {
             double c[5];
 #pragma unroll
-            for (int k = 0; k < 5; k++) c[k] = C[(size_t)k * Lg + x];
+            for (int k = 0; k < 5; k++) c[k] = C[k * Lg + x];
             double total = 0;
 #pragma unroll
             for (int k = 0; k < 5; k++) total = __dadd_rn(total, c[k]);
@@ -209,51 +276,48 @@ __global__ void __launch_bounds__(kThreads) fb_em_kernel(const Params prm) {
 #pragma unroll
             for (int k = 0; k < 4; k++) p[k] = (total != 0.0) ? __ddiv_rn(__dadd_rn(c[k], nq), total) : 0.25;
             errRow(m.etp, p, e);
-#pragma unroll
-            for (int k = 0; k < 4; k++) P[(size_t)k * rows + F + x] = p[k];
-#pragma unroll
-            for (int k = 0; k < 5; k++) E[(size_t)k * rows + F + x] = e[k];
+            storeRow(5 + x, p, e);
         }
     };
     if (it.kind == FB_ITEM_EM && (it.flags & FB_FLAG_RESUME)) { mstep(); __syncthreads(); }
 
-    // ---- read chunking: W holds [reads of the chunk][stride] doubles
-    const int maxLen = it.max_len;
-    const int stride = unm ? (maxLen + Lg - 1) : (maxLen - 1);
-    const int strideP = max(stride, 1);
-    const int chunkReads = max(1, wCap / strideP);
-    const int cpr = (strideP + 31) / 32;     // 32-offset units per read
-
-    // pass-2 style scoring of reads [q0,q1) into W, then per-read first-max
+    // ---- pass 2: products of exact table entries against the gap string, first maximum, accept, unit votes
     auto pass2 = [&](int slot, bool finalizeRef, bool vote) {
         for (int q0 = 0; q0 < R; q0 += chunkReads) {
             const int q1 = min(R, q0 + chunkReads);
+            if (!singleChunk) { stageReads(q0, q1); __syncthreads(); }
             const int units = (q1 - q0) * cpr;
             for (int u = warp; u < units; u += kWarps) {
                 const int ql = u / cpr, ch = u - ql * cpr;
                 const int qi = g.read_begin + q0 + ql;
                 const int len = prm.read_len[qi], fl = prm.read_flags[qi], rel = prm.read_mate[qi];
-                const unsigned char* rd = prm.codes + prm.read_off[qi];
                 const int jlo = prm.read_jlo[qi], jhi = len - prm.read_jcut[qi];
                 int lo, hi; window(g, fl, len, Lg, &lo, &hi);
-                const int x0 = lo + ch * 32 + lane;
-                double p = -1.0;
-                int t;
-                const bool act = (x0 <= hi) && (strideP > ch * 32 + lane) && admissible(m, g, fl, rel, len, x0, Lg, finalizeRef, &t);
-                if (act) {
-                    p = 1.0;
+                const int ia = ch * 64 + lane, ib = ia + 32;
+                const int xa = lo + ia, xb = lo + ib;
+                int ta, tb;
+                const bool acta = (xa <= hi) && admissible(m, g, fl, rel, len, xa, Lg, finalizeRef, &ta);
+                const bool actb = (xb <= hi) && admissible(m, g, fl, rel, len, xb, Lg, finalizeRef, &tb);
+                const unsigned ma = __ballot_sync(0xffffffffu, acta), mb = __ballot_sync(0xffffffffu, actb);
+                double pa = 1.0, pb = 1.0;
+                if (ma | mb) {
+                    const int ra = acta ? xa + F : (actb ? xb + F : F), rb = actb ? xb + F : ra;
                     const bool rev = fl & FB_READ_REVERSE;
-                    const unsigned char* gs = G + (x0 + F);
+                    const unsigned char* rc = RC + ql * mlp;
+                    const unsigned char* ga = G + ra; const unsigned char* gb = G + rb;
+#pragma unroll 2
                     for (int j = jlo; j < jhi; j++) {
-                        const int to = rd[j], from = gs[j];
-                        const int k = rev ? (len - j - 1) : j;
-                        const double f = (from == to) ? m.match[k] : m.mism[k * 25 + from * 5 + to];
-                        p = __dmul_rn(p, f);
+                        const int c = rc[j];
+                        const double2 mk = MT2[rev ? (len - j - 1) : j];      // x = 1-e-ins-del, y = e
+                        const int fa = ga[j], fb = gb[j];
+                        const double va = (fa == c) ? mk.x : __dmul_rn(mk.y, ETP[fa * 5 + c]);
+                        const double vb = (fb == c) ? mk.x : __dmul_rn(mk.y, ETP[fb * 5 + c]);
+                        pa = __dmul_rn(pa, va); pb = __dmul_rn(pb, vb);
                     }
+                    if (lane == 0) { const unsigned n = __popc(ma) + __popc(mb); atomicAdd(&s_place2, (unsigned long long)n); atomicAdd(&s_terms, (unsigned long long)n * (unsigned long long)(jhi - jlo)); }
                 }
-                const unsigned act_mask = __ballot_sync(0xffffffffu, act);
-                if (lane == 0 && act_mask) { atomicAdd(&s_place2, (unsigned long long)__popc(act_mask)); atomicAdd(&s_terms, (unsigned long long)__popc(act_mask) * (unsigned long long)(jhi - jlo)); }
-                if (ch * 32 + lane < strideP) W[(size_t)ql * strideP + ch * 32 + lane] = p;
+                if (ia < strideP) W[ql * strideP + ia] = acta ? pa : -1.0;
+                if (ib < strideP) W[ql * strideP + ib] = actb ? pb : -1.0;
             }
             __syncthreads();
             // first maximum over ascending offsets (strict >), accept test, unit votes (Figbird.cpp:3787-3912)
@@ -263,7 +327,7 @@ __global__ void __launch_bounds__(kThreads) fb_em_kernel(const Params prm) {
                 int lo, hi; window(g, fl, len, Lg, &lo, &hi);
                 const int n = hi - lo + 1;
                 double best = -1.0; int bestI = 0x7fffffff;
-                for (int i = lane; i < n; i += 32) { double v = W[(size_t)ql * strideP + i]; if (v > best) { best = v; bestI = i; } }
+                for (int i = lane; i < n; i += 32) { double v = W[ql * strideP + i]; if (v > best) { best = v; bestI = i; } }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     double ov = __shfl_xor_sync(0xffffffffu, best, o); int oi = __shfl_xor_sync(0xffffffffu, bestI, o);
@@ -272,8 +336,8 @@ __global__ void __launch_bounds__(kThreads) fb_em_kernel(const Params prm) {
                 const int bestx = (best >= 0) ? lo + bestI : 0;
                 if (lane == 0) { oP2[(size_t)slot * R + q] = best; oPos[(size_t)slot * R + q] = bestx; }
                 if (vote && unm && best >= m.accept_min_p) {
-                    const unsigned char* rd = prm.codes + prm.read_off[qi];
-                    for (int j = lane; j < len; j += 32) { int x = bestx + j; if (x >= 0 && x < Lg) atomicAdd(&NC[(size_t)rd[j] * Lg + x], 1); }
+                    const unsigned char* rc = RC + ql * mlp;
+                    for (int j = lane; j < len; j += 32) { int x = bestx + j; if (x >= 0 && x < Lg) atomicAdd(&NC[rc[j] * Lg + x], 1); }
                     if (lane == 0 && g.orig_len <= 30) {
                         int fo = 0; const int p0 = bestx, val = p0 + len - Lg;
                         if (p0 < 0 && val > 0 && -p0 > 3 && val > 3) fo |= 4;
@@ -294,6 +358,7 @@ __global__ void __launch_bounds__(kThreads) fb_em_kernel(const Params prm) {
     } else {
         const int maxCalls = it.max_rounds + ((it.flags & FB_FLAG_EXTRA_PASS) ? 1 : 0);
         bool emDone = it.max_rounds <= 0;
+        const int split = pl.split;
         for (int call = 0; call < maxCalls; call++) {
             const bool extra = emDone;
             const int slot = (it.flags & FB_FLAG_RECORD_ALL) ? call : 0;
@@ -303,85 +368,97 @@ __global__ void __launch_bounds__(kThreads) fb_em_kernel(const Params prm) {
             // ================= pass 1 (Figbird.cpp:3082-3263, 3530-3689) =================
             for (int q0 = 0; q0 < R; q0 += chunkReads) {
                 const int q1 = min(R, q0 + chunkReads);
+                if (!singleChunk) { stageReads(q0, q1); __syncthreads(); }
                 const int units = (q1 - q0) * cpr;
                 for (int u = warp; u < units; u += kWarps) {
                     const int ql = u / cpr, ch = u - ql * cpr;
                     const int qi = g.read_begin + q0 + ql;
                     const int len = prm.read_len[qi], fl = prm.read_flags[qi], rel = prm.read_mate[qi];
-                    const unsigned char* rd = prm.codes + prm.read_off[qi];
                     const int jlo = prm.read_jlo[qi], jhi = len - prm.read_jcut[qi];
                     int lo, hi; window(g, fl, len, Lg, &lo, &hi);
-                    const int x0 = lo + ch * 32 + lane;
-                    int t;
-                    const bool act = (x0 <= hi) && (strideP > ch * 32 + lane) && admissible(m, g, fl, rel, len, x0, Lg, false, &t);
-                    double w = 0.0, p = 0.0;
-                    if (act) {
-                        p = unm ? m.pdf[min(max(t, 0), m.n_insert - 1)] : 1.0;
+                    const int ia = ch * 64 + lane, ib = ia + 32;
+                    const int xa = lo + ia, xb = lo + ib;
+                    int ta = 0, tb = 0;
+                    const bool acta = (xa <= hi) && admissible(m, g, fl, rel, len, xa, Lg, false, &ta);
+                    const bool actb = (xb <= hi) && admissible(m, g, fl, rel, len, xb, Lg, false, &tb);
+                    const unsigned ma = __ballot_sync(0xffffffffu, acta), mb = __ballot_sync(0xffffffffu, actb);
+                    double wa = 0.0, wb = 0.0, pa = 0.0, pb = 0.0;
+                    if (ma | mb) {
+                        const int ra = acta ? xa + F : (actb ? xb + F : F), rb = actb ? xb + F : ra;
+                        pa = (unm && acta) ? m.pdf[min(max(ta, 0), m.n_insert - 1)] : 1.0;
+                        pb = (unm && actb) ? m.pdf[min(max(tb, 0), m.n_insert - 1)] : 1.0;
                         const bool rev = fl & FB_READ_REVERSE;
-                        const double* Pr = P + (x0 + F);
-                        const double* Er = E + (x0 + F);
+                        const unsigned char* rc = RC + ql * mlp;
+                        const unsigned short* sa = RS + ra; const unsigned short* sb = RS + rb;
+#pragma unroll 2
                         for (int j = jlo; j < jhi; j++) {
-                            const int c = rd[j];
-                            const int k = rev ? (len - 1 - j) : j;
-                            const double ek = m.e[k];
-                            double term;
-                            if (c < 4) term = __dadd_rn(__dmul_rn(Pr[(size_t)c * rows + j], m.ome[k]), __dmul_rn(ek, Er[(size_t)c * rows + j]));
-                            else term = __dmul_rn(ek, Er[(size_t)4 * rows + j]);
-                            p = __dmul_rn(p, term);
+                            const int cb = rc[j] * S;
+                            const double2 mk = MT1[rev ? (len - 1 - j) : j];      // x = 1-e, y = e
+                            const double2 va = UT[cb + sa[j]];
+                            const double2 vb = UT[cb + sb[j]];
+                            pa = __dmul_rn(pa, __dadd_rn(__dmul_rn(va.x, mk.x), __dmul_rn(mk.y, va.y)));
+                            pb = __dmul_rn(pb, __dadd_rn(__dmul_rn(vb.x, mk.x), __dmul_rn(mk.y, vb.y)));
                         }
-                        if (p > 0.0) {
-                            if (unm) { const double s = log10(p); w = exp(0.5 * s); }     // Figbird.cpp:3591,3601
-                            else {
-                                // Figbird.cpp:3169,3179: w = pow(10, ln p).  These weights run down into the subnormal range and
-                                // the reference's consensus still sees them (a row whose only vote is 4.9e-324 gets that base),
-                                // so gradual underflow must round like glibc's pow: evaluate 300 decades higher (exact shift of
-                                // the exponent argument) and let one IEEE multiply do the final, correctly rounded, scaling.
-                                const double s = log(p);
-                                w = (s < -290.0) ? __dmul_rn(pow(10.0, s + 300.0), 1e-300) : pow(10.0, s);
-                            }
-                        } else p = 0.0;
-                    }
-                    // per-read maximum of the raw product (positive doubles order like their bit patterns)
-                    double pm = p;
+                        if (acta && pa > 0.0) wa = placementWeight(pa, unm); else pa = 0.0;
+                        if (actb && pb > 0.0) wb = placementWeight(pb, unm); else pb = 0.0;
+                        // per-read maximum of the raw product (positive doubles order like their bit patterns)
+                        double pm = fmax(pa, pb);
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) pm = fmax(pm, __shfl_xor_sync(0xffffffffu, pm, o));
-                    const unsigned act_mask = __ballot_sync(0xffffffffu, act);
-                    if (lane == 0 && act_mask) {
-                        if (pm > 0.0) atomicMax((unsigned long long*)&oP1[(size_t)slot * R + q0 + ql], (unsigned long long)__double_as_longlong(pm));
-                        atomicAdd(&s_place1, (unsigned long long)__popc(act_mask));
-                        atomicAdd(&s_terms, (unsigned long long)__popc(act_mask) * (unsigned long long)(jhi - jlo));
+                        for (int o = 16; o > 0; o >>= 1) pm = fmax(pm, __shfl_xor_sync(0xffffffffu, pm, o));
+                        if (lane == 0) {
+                            if (pm > 0.0) atomicMax((unsigned long long*)&oP1[(size_t)slot * R + q0 + ql], (unsigned long long)__double_as_longlong(pm));
+                            const unsigned n = __popc(ma) + __popc(mb);
+                            atomicAdd(&s_place1, (unsigned long long)n);
+                            atomicAdd(&s_terms, (unsigned long long)n * (unsigned long long)(jhi - jlo));
+                        }
                     }
-                    if (ch * 32 + lane < strideP) W[(size_t)ql * strideP + ch * 32 + lane] = w;
+                    if (ia < strideP) W[ql * strideP + ia] = wa;
+                    if (ib < strideP) W[ql * strideP + ib] = wb;
                 }
                 __syncthreads();
-                // gather the weights of this chunk into the gap rows, fixed order: read ascending, read base ascending
-                for (int x = tid; x < Lg; x += kThreads) {
+                // gather the weights of this chunk into the gap rows in a fixed order (deterministic, no FP atomics):
+                // thread (row x, part s) sums reads s, s+split, ... ascending, read base ascending; parts are added in order.
+                for (int idx = tid; idx < Lg * split; idx += kThreads) {
+                    const int s = idx / Lg, x = idx - s * Lg;
                     double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
-                    for (int ql = 0; ql < q1 - q0; ql++) {
+                    for (int ql = s; ql < q1 - q0; ql += split) {
                         const int qi = g.read_begin + q0 + ql;
                         const int len = prm.read_len[qi], fl = prm.read_flags[qi];
-                        const unsigned char* rd = prm.codes + prm.read_off[qi];
+                        const unsigned char* rc = RC + ql * mlp;
                         int lo, hi; window(g, fl, len, Lg, &lo, &hi);
                         // x0 = x - j in [lo, hi]  <=>  j in [x - hi, x - lo]
                         const int ja = max(0, x - hi), jb = min(len - 1, x - lo);
-                        const double* wr = W + (size_t)ql * strideP - lo;
+                        const double* wr = W + ql * strideP - lo;
                         for (int j = ja; j <= jb; j++) {
                             const double w = wr[x - j];
-                            switch (rd[j]) { case 0: a0 = __dadd_rn(a0, w); break; case 1: a1 = __dadd_rn(a1, w); break; case 2: a2 = __dadd_rn(a2, w); break; case 3: a3 = __dadd_rn(a3, w); break; default: a4 = __dadd_rn(a4, w); }
+                            switch (rc[j]) { case 0: a0 = __dadd_rn(a0, w); break; case 1: a1 = __dadd_rn(a1, w); break; case 2: a2 = __dadd_rn(a2, w); break; case 3: a3 = __dadd_rn(a3, w); break; default: a4 = __dadd_rn(a4, w); }
                         }
                     }
-                    C[x] = __dadd_rn(C[x], a0); C[(size_t)Lg + x] = __dadd_rn(C[(size_t)Lg + x], a1); C[(size_t)2 * Lg + x] = __dadd_rn(C[(size_t)2 * Lg + x], a2);
-                    C[(size_t)3 * Lg + x] = __dadd_rn(C[(size_t)3 * Lg + x], a3); C[(size_t)4 * Lg + x] = __dadd_rn(C[(size_t)4 * Lg + x], a4);
+                    if (split == 1) {
+                        C[x] = __dadd_rn(C[x], a0); C[Lg + x] = __dadd_rn(C[Lg + x], a1); C[2 * Lg + x] = __dadd_rn(C[2 * Lg + x], a2);
+                        C[3 * Lg + x] = __dadd_rn(C[3 * Lg + x], a3); C[4 * Lg + x] = __dadd_rn(C[4 * Lg + x], a4);
+                    } else {
+                        double* gp = GP + (size_t)s * 5 * Lg + x;
+                        gp[0] = a0; gp[Lg] = a1; gp[2 * Lg] = a2; gp[3 * Lg] = a3; gp[4 * Lg] = a4;
+                    }
+                }
+                if (split > 1) {
+                    __syncthreads();
+                    for (int i = tid; i < 5 * Lg; i += kThreads) {
+                        double a = C[i];
+                        for (int s = 0; s < split; s++) a = __dadd_rn(a, GP[(size_t)s * 5 * Lg + i]);
+                        C[i] = a;
+                    }
                 }
                 __syncthreads();
             }
-            // pass-1 maxima: bit pattern 0 means no admissible offset -> -1
-            for (int q = tid; q < R; q += kThreads) { double v = __ldcg(&oP1[(size_t)slot * R + q]); if (!(v > 0.0)) oP1[(size_t)slot * R + q] = -1.0; }   // atomics live in L2: bypass L1
+            // pass-1 maxima: bit pattern 0 means no admissible offset -> -1 (the atomics live in L2: bypass L1)
+            for (int q = tid; q < R; q += kThreads) { double v = __ldcg(&oP1[(size_t)slot * R + q]); if (!(v > 0.0)) oP1[(size_t)slot * R + q] = -1.0; }
             // ================= computeSequence(0,0) =================
             for (int x = tid; x < Lg; x += kThreads) {
                 double mx = 0; int mi = -1;
 #pragma unroll
-                for (int k = 0; k < 5; k++) { double v = C[(size_t)k * Lg + x]; if (v > mx) { mx = v; mi = k; } }
+                for (int k = 0; k < 5; k++) { double v = C[k * Lg + x]; if (v > mx) { mx = v; mi = k; } }
                 unsigned char c = (mi >= 0 && mi < 4) ? (unsigned char)mi : 4;
                 G[F + x] = c; oSoft[x] = c;
             }
@@ -396,7 +473,7 @@ __global__ void __launch_bounds__(kThreads) fb_em_kernel(const Params prm) {
                 for (int x = tid; x < Lg; x += kThreads) {
                     int mx = 0, mi = -1;
 #pragma unroll
-                    for (int k = 0; k < 5; k++) { int v = it.tables_in_smem ? NC[(size_t)k * Lg + x] : __ldcg(&NC[(size_t)k * Lg + x]); if (v > mx) { mx = v; mi = k; } }
+                    for (int k = 0; k < 5; k++) { int v = TSMEM ? NC[k * Lg + x] : __ldcg(&NC[k * Lg + x]); if (v > mx) { mx = v; mi = k; } }
                     unsigned char h = (mx > 0 && mi >= 0 && mi < 4) ? (unsigned char)mi : 4;
                     oHard[x] = h; oCov[x] = mx;
                     if (!prevValid || PREV[x] != h) same = 0;
@@ -423,7 +500,7 @@ __global__ void __launch_bounds__(kThreads) fb_em_kernel(const Params prm) {
         }
         if (it.off_counts >= 0) {
             double* oc = (double*)(out + it.off_counts);
-            for (int i = tid; i < 5 * Lg; i += kThreads) { int x = i / 5, k = i % 5; oc[i] = C[(size_t)k * Lg + x]; }
+            for (int i = tid; i < 5 * Lg; i += kThreads) { int x = i / 5, k = i % 5; oc[i] = C[k * Lg + x]; }
         }
     }
     __syncthreads();
@@ -461,10 +538,12 @@ struct fb_ctx {
     std::string err;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t bstream[kNumBuckets + 1] = {};   // one stream per shared-memory bucket (+1: global-table items)
+    cudaEvent_t bev[kNumBuckets + 1] = {};
     int smemOptin = 0;
     bool haveModel = false, haveBatch = false;
     DevModel dm{};
-    DevBuf<double> d_e, d_ome, d_match, d_mism, d_pdf;
+    DevBuf<double> d_e, d_ome, d_match, d_pdf;
     std::vector<DevGap> hGaps; std::vector<int> hGapMaxLen;
     DevBuf<DevGap> d_gaps; DevBuf<int> d_rlen, d_rmate, d_pl, d_pr; DevBuf<long long> d_roff;
     DevBuf<unsigned char> d_rfl, d_jlo, d_jcut, d_codes, d_flank;
@@ -492,7 +571,9 @@ extern "C" fb_status fb_ctx_create(int32_t device, fb_ctx** out) {
     c->smemOptin = (int)pr.sharedMemPerBlockOptin;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
-    CK(cudaFuncSetAttribute(fb_em_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CK(cudaFuncSetAttribute(fb_em_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CK(cudaFuncSetAttribute(fb_em_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    for (int b = 0; b <= kNumBuckets; b++) { CK(cudaStreamCreateWithFlags(&c->bstream[b], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->bev[b], cudaEventDisableTiming)); }
     CK(c->d_ctr.ensure(4)); CK(cudaMemset(c->d_ctr.p, 0, 4 * sizeof(unsigned long long)));
     return FB_OK;
 }
@@ -501,12 +582,13 @@ extern "C" void fb_ctx_destroy(fb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    c->d_e.release(); c->d_ome.release(); c->d_match.release(); c->d_mism.release(); c->d_pdf.release();
+    c->d_e.release(); c->d_ome.release(); c->d_match.release(); c->d_pdf.release();
     c->d_gaps.release(); c->d_rlen.release(); c->d_rmate.release(); c->d_pl.release(); c->d_pr.release(); c->d_roff.release();
     c->d_rfl.release(); c->d_jlo.release(); c->d_jcut.release(); c->d_codes.release(); c->d_flank.release();
     c->d_items.release(); c->d_in.release(); c->d_out.release(); c->d_scratch.release(); c->d_ctr.release();
     if (c->h_out) cudaFreeHost(c->h_out);
     if (c->h_in) cudaFreeHost(c->h_in);
+    for (int b = 0; b <= kNumBuckets; b++) { if (c->bstream[b]) cudaStreamDestroy(c->bstream[b]); if (c->bev[b]) cudaEventDestroy(c->bev[b]); }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -523,20 +605,18 @@ extern "C" fb_status fb_model_upload(fb_ctx* c, const FbModel* m) {
     if (!c || !m || m->max_read_len <= 0 || m->n_insert <= 0) return FB_ERR_ARG;
     CK(cudaSetDevice(c->device));
     const int RL = m->max_read_len;
-    std::vector<double> ome(RL), match(RL), mism((size_t)RL * 25);
+    std::vector<double> ome(RL), match(RL);
     for (int k = 0; k < RL; k++) {
         ome[k] = 1 - m->err_pos[k];
         match[k] = 1 - m->err_pos[k] - m->ins_pos[k] - m->del_pos[k];                 // Figbird.cpp:3400
-        for (int f = 0; f < 5; f++) for (int t = 0; t < 5; t++) mism[(size_t)k * 25 + f * 5 + t] = m->err_pos[k] * m->err_type[f * 5 + t];   // :3405
     }
     fb_status s;
     if ((s = upload(c, c->d_e, m->err_pos, RL))) return s;
     if ((s = upload(c, c->d_ome, ome.data(), RL))) return s;
     if ((s = upload(c, c->d_match, match.data(), RL))) return s;
-    if ((s = upload(c, c->d_mism, mism.data(), mism.size()))) return s;
     if ((s = upload(c, c->d_pdf, m->insert_pdf, m->n_insert))) return s;
     CK(cudaStreamSynchronize(c->stream));
-    c->dm.e = c->d_e.p; c->dm.ome = c->d_ome.p; c->dm.match = c->d_match.p; c->dm.mism = c->d_mism.p; c->dm.pdf = c->d_pdf.p; c->dm.n_insert = m->n_insert;
+    c->dm.e = c->d_e.p; c->dm.ome = c->d_ome.p; c->dm.match = c->d_match.p; c->dm.pdf = c->d_pdf.p; c->dm.n_insert = m->n_insert;
     memcpy(c->dm.etp, m->err_type, sizeof c->dm.etp);
     c->dm.tmin = m->insert_min; c->dm.tmax = m->insert_max; c->dm.max_read_len = RL;
     // accept iff -log10(p) < cutoff (Figbird.cpp:3474,3852).  log10 is monotone, so the accepted set is
@@ -608,14 +688,16 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
     auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
     std::vector<DevItem> di(n);
     size_t outTotal = 0, inTotal = 0, scratchTotal = 0;
-    int smemNeed = kMinW;
+    std::vector<int> bucketOf(n, 0);
+    int bucketSmem[kNumBuckets + 1] = {0, 0, 0, 0, 0};
+    int bucketCount[kNumBuckets + 1] = {0, 0, 0, 0, 0};
     for (int i = 0; i < n; i++) {
         const FbWorkItem& it = items[i];
-        if (it.gap < 0 || it.gap >= (int)c->hGaps.size() || it.cand_len < 0) { c->err = "bad work item"; return FB_ERR_ARG; }
+        if (it.gap < 0 || it.gap >= (int)c->hGaps.size() || it.cand_len < 0 || it.cand_len > 60000) { c->err = "bad work item"; return FB_ERR_ARG; }
         const DevGap& g = c->hGaps[it.gap];
         DevItem d{};
         d.kind = it.kind; d.gap = it.gap; d.Lg = it.cand_len; d.max_rounds = it.max_rounds; d.flags = it.flags; d.comp_in = it.comp_count_in;
-        const int Lg = it.cand_len, R = g.n_reads, rows = Lg + 2 * g.flank_len;
+        const int Lg = it.cand_len, R = g.n_reads;
         int slots = 1;
         if (it.kind == FB_ITEM_EM && (it.flags & FB_FLAG_RECORD_ALL)) slots = it.max_rounds + ((it.flags & FB_FLAG_EXTRA_PASS) ? 1 : 0);
         d.n_slots = slots;
@@ -635,27 +717,50 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
             d.counts_in_off = (long long)inTotal; inTotal += al(sizeof(double) * 5 * Lg);
         }
         if (it.string_in && Lg > 0) { d.string_in_off = (long long)inTotal; inTotal += al(Lg); }
-        // shared-memory plan: tables if they leave >= kMinW for W, else global scratch
-        const size_t tb = al((size_t)rows * 9 * 8 + (size_t)Lg * 5 * 8 + (size_t)Lg * 5 * 4 + rows + Lg);
+        // shared-memory plan: tables + model + at least one read's chunk must fit, else tables go to global scratch
         const int ml = c->hGapMaxLen[it.gap];
         d.max_len = ml;
-        const size_t stride = (g.mode == FB_MODE_UNMAPPED) ? (size_t)(ml + Lg - 1) : (size_t)(ml - 1);
-        const size_t wWant = std::min<size_t>(std::max<size_t>(stride, 1) * 8 * (size_t)std::max(R, 1), 96 * 1024);
-        if (tb + kMinW <= (size_t)kMaxSmem) {
+        const Plan pl = makePlan(Lg, g.flank_len, c->dm.max_read_len, ml, g.mode);
+        const long long want = std::min<long long>((long long)pl.perRead * std::max(R, 1), kChunkWant);
+        const long long chunk = std::max<long long>(want, pl.perRead) + 32;
+        if ((long long)pl.tableBytes + pl.localFixed + pl.perRead + 32 <= kMaxSmem) {
             d.tables_in_smem = 1; d.scratch_off = -1;
-            smemNeed = std::max<int>(smemNeed, (int)std::min<size_t>(kMaxSmem, tb + std::max<size_t>(wWant, kMinW)));
+            const int need = (int)std::min<long long>(kMaxSmem, (long long)pl.tableBytes + pl.localFixed + chunk);
+            int b = 0; while (b < kNumBuckets - 1 && need > bucketCap(b)) b++;
+            bucketOf[i] = b; bucketSmem[b] = std::max(bucketSmem[b], need);
         } else {
-            d.tables_in_smem = 0; d.scratch_off = (long long)scratchTotal; scratchTotal += tb;
-            smemNeed = std::max<int>(smemNeed, (int)std::min<size_t>(kMaxSmem, std::max<size_t>(wWant, std::max<size_t>(stride, 1) * 8 + 64)));
-            if (std::max<size_t>(stride, 1) * 8 > (size_t)kMaxSmem) { c->err = "candidate length too large for one weight row in shared memory"; return FB_ERR_ARG; }
+            if ((long long)pl.localFixed + pl.perRead + 32 > kMaxSmem) { c->err = "candidate length too large for one weight row in shared memory"; return FB_ERR_ARG; }
+            d.tables_in_smem = 0; d.scratch_off = (long long)scratchTotal; scratchTotal += (size_t)pl.tableBytes;
+            bucketOf[i] = kNumBuckets; bucketSmem[kNumBuckets] = std::max(bucketSmem[kNumBuckets], (int)std::min<long long>(kMaxSmem, (long long)pl.localFixed + chunk));
         }
+        bucketCount[bucketOf[i]]++;
         di[i] = d;
+    }
+    // launch order: per bucket, longest chains first (unmapped EM items with many reads), so the tail is short
+    std::vector<int> order(n);
+    int bucketBegin[kNumBuckets + 2];
+    {
+        int acc = 0;
+        for (int b = 0; b <= kNumBuckets; b++) { bucketBegin[b] = acc; acc += bucketCount[b]; }
+        bucketBegin[kNumBuckets + 1] = acc;
+        int fill[kNumBuckets + 1];
+        for (int b = 0; b <= kNumBuckets; b++) fill[b] = bucketBegin[b];
+        for (int i = 0; i < n; i++) order[fill[bucketOf[i]]++] = i;
+        auto cost = [&](int i) {
+            const DevGap& g = c->hGaps[items[i].gap];
+            const double rounds = items[i].kind == FB_ITEM_HARD ? 0.3 : (g.mode == FB_MODE_UNMAPPED ? 12.0 : 3.0);
+            return rounds * (double)g.n_reads * (double)(items[i].cand_len + 100);
+        };
+        for (int b = 0; b <= kNumBuckets; b++)
+            std::stable_sort(order.begin() + bucketBegin[b], order.begin() + bucketBegin[b + 1], [&](int x, int y) { return cost(x) > cost(y); });
     }
     // ---- stage inputs
     const size_t itemsBytes = al(sizeof(DevItem) * (size_t)n);
-    const size_t inBytes = itemsBytes + inTotal + 16;
+    const size_t orderOff = itemsBytes + al(inTotal);
+    const size_t inBytes = orderOff + al(sizeof(int) * (size_t)n) + 16;
     if (inBytes > c->h_in_cap) { if (c->h_in) cudaFreeHost(c->h_in); c->h_in = nullptr; c->h_in_cap = 0; size_t want = inBytes + inBytes / 2; CK(cudaMallocHost((void**)&c->h_in, want)); c->h_in_cap = want; }
     memcpy(c->h_in, di.data(), sizeof(DevItem) * (size_t)n);
+    memcpy(c->h_in + orderOff, order.data(), sizeof(int) * (size_t)n);
     for (int i = 0; i < n; i++) {
         const FbWorkItem& it = items[i];
         if (di[i].counts_in_off >= 0) memcpy(c->h_in + itemsBytes + di[i].counts_in_off, it.counts_in, sizeof(double) * 5 * (size_t)it.cand_len);
@@ -674,18 +779,29 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
     prm.read_flags = c->d_rfl.p; prm.read_jlo = c->d_jlo.p; prm.read_jcut = c->d_jcut.p; prm.codes = c->d_codes.p;
     prm.flank = c->d_flank.p; prm.pile_l = c->d_pl.p; prm.pile_r = c->d_pr.p;
     prm.items = (const DevItem*)c->d_in.p; prm.in_arena = c->d_in.p + itemsBytes; prm.out_arena = c->d_out.p; prm.scratch = c->d_scratch.p;
-    prm.counters = c->d_ctr.p; prm.smem_bytes = smemNeed;
+    prm.counters = c->d_ctr.p;
 
+    // one launch per shared-memory bucket, on its own stream, so small items run at high occupancy beside large ones
     CK(cudaEventRecord(c->ev0, c->stream));
-    fb_em_kernel<<<n, kThreads, smemNeed, c->stream>>>(prm);
-    CK(cudaGetLastError());
+    int launches = 0;
+    const int* d_order = (const int*)(c->d_in.p + orderOff);
+    for (int b = 0; b <= kNumBuckets; b++) {
+        if (!bucketCount[b]) continue;
+        CK(cudaStreamWaitEvent(c->bstream[b], c->ev0, 0));
+        if (b < kNumBuckets) fb_em_kernel<true><<<bucketCount[b], kThreads, bucketSmem[b], c->bstream[b]>>>(prm, d_order + bucketBegin[b], bucketSmem[b]);
+        else fb_em_kernel<false><<<bucketCount[b], kThreads, bucketSmem[b], c->bstream[b]>>>(prm, d_order + bucketBegin[b], bucketSmem[b]);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(c->bev[b], c->bstream[b]));
+        CK(cudaStreamWaitEvent(c->stream, c->bev[b], 0));
+        launches++;
+    }
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaMemcpyAsync(c->h_out, c->d_out.p, outTotal, cudaMemcpyDeviceToHost, c->stream));
     unsigned long long hc[4] = {0, 0, 0, 0};
     CK(cudaMemcpyAsync(hc, c->d_ctr.p, sizeof hc, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    c->ctr.device_ms += ms; c->ctr.kernel_launches += 1; c->ctr.d2h_bytes += (int64_t)outTotal;
+    c->ctr.device_ms += ms; c->ctr.kernel_launches += launches; c->ctr.d2h_bytes += (int64_t)outTotal;
     c->ctr.placements_p1 = (int64_t)hc[0]; c->ctr.placements_p2 = (int64_t)hc[1]; c->ctr.base_terms = (int64_t)hc[2];
     for (int i = 0; i < n; i++) {
         FbItemOut* H = (FbItemOut*)(c->h_out + di[i].out_off);
