@@ -17,6 +17,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <thread>
+#include <time.h>
 
 #include "fb_gapfiller.h"
 #include "fb_io.h"
@@ -42,6 +43,8 @@ public:
         if (!reqs_.empty() && (int)reqs_.size() >= running_) flush(lk);
     }
     int64_t ticks() const { return ticks_; }
+    double engineSeconds() const { return tEngine_; }
+    double copySeconds() const { return tCopy_; }
 
 private:
     struct Req { int gap; const std::vector<ItemSpec>* items; std::vector<ItemResult>* results; bool done; };
@@ -55,7 +58,10 @@ private:
             wi.push_back(w);
         }
         std::vector<const FbItemOut*> outs(wi.size(), nullptr);
+        auto c0 = std::chrono::steady_clock::now();
         fb_status st = wi.empty() ? FB_OK : fb_em_run(ctx_, wi.data(), (int32_t)wi.size(), outs.data());
+        auto c1 = std::chrono::steady_clock::now();
+        tEngine_ += std::chrono::duration<double>(c1 - c0).count();
         ticks_++;
         if (st != FB_OK) { failed_ = true; err_ = std::string("fb_em_run failed: ") + fb_last_error(ctx_); }
         size_t k = 0;
@@ -80,6 +86,7 @@ private:
             }
             r->done = true;
         }
+        tCopy_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - c1).count();
         cv_.notify_all();
     }
     fb_ctx* ctx_;
@@ -88,6 +95,7 @@ private:
     int running_;
     bool failed_ = false; std::string err_;
     int64_t ticks_ = 0;
+    double tEngine_ = 0, tCopy_ = 0;
 };
 
 static bool parseArgs(int argc, const char* const* argv, Args& a) {
@@ -116,7 +124,7 @@ static std::vector<int> visibleDevices() {
     return d;
 }
 
-struct RunStats { double tLoad = 0, tModel = 0, tPrep = 0, tFill = 0, tWrite = 0; int64_t refPlacements = 0; FbCounters dev{}; int64_t ticks = 0; };
+struct RunStats { double tLoad = 0, tModel = 0, tPrep = 0, tFill = 0, tWrite = 0, tEngine = 0, tCopy = 0, tCtx = 0, tWorkers = 0, cpuWorkers = 0; int64_t refPlacements = 0; FbCounters dev{}; int64_t ticks = 0; };
 
 int fillgapsMain(int argc, const char* const* argv) {
     using clk = std::chrono::steady_clock;
@@ -179,11 +187,12 @@ int fillgapsMain(int argc, const char* const* argv) {
         for (auto& sh : shard) { std::vector<int> keep; for (int g : sh) if (onlyGap[g]) keep.push_back(g); sh.swap(keep); }
     }
     std::vector<std::string> devErr(nD);
-    std::vector<FbCounters> devCtr(nD); std::vector<int64_t> devTicks(nD, 0);
+    std::vector<FbCounters> devCtr(nD); std::vector<int64_t> devTicks(nD, 0); std::vector<double> devEng(nD, 0), devCopy(nD, 0), devCtx(nD, 0), devWork(nD, 0), devCpu(nD, 0);
     std::vector<std::thread> devThreads;
     for (int d = 0; d < nD; d++) devThreads.emplace_back([&, d] {
         const std::vector<int>& mine = shard[d];
         if (mine.empty()) return;
+        auto d0 = clk::now();
         fb_ctx* ctx = nullptr;
         if (fb_ctx_create(devs[d], &ctx) != FB_OK || !ctx) { devErr[d] = std::string("fb_ctx_create failed on device ") + std::to_string(devs[d]) + ": " + (ctx ? fb_last_error(ctx) : "no context"); if (ctx) fb_ctx_destroy(ctx); return; }
         FbModel fm{};
@@ -219,6 +228,8 @@ int fillgapsMain(int argc, const char* const* argv) {
         B.n_flank = (int64_t)flank.size(); B.flank_codes = flank.data(); B.n_pile_rows = (int64_t)(pileL.size() / 4); B.pile_left = pileL.data(); B.pile_right = pileR.data();
         if (fb_batch_upload(ctx, &B) != FB_OK) { devErr[d] = std::string("fb_batch_upload: ") + fb_last_error(ctx); fb_ctx_destroy(ctx); return; }
 
+        auto d1 = clk::now();
+        devCtx[d] = secs(d0, d1);
         int inflight = 512;
         if (const char* e = getenv("FIGBIRD_INFLIGHT")) inflight = std::max(1, atoi(e));
         const int workers = std::max(1, std::min((int)mine.size(), inflight));
@@ -226,14 +237,17 @@ int fillgapsMain(int argc, const char* const* argv) {
         std::atomic<int> next(0);
         std::vector<std::thread> th;
         std::mutex emu;
+        std::atomic<long long> cpuNs(0);
         for (int w = 0; w < workers; w++) th.emplace_back([&] {
             try {
                 for (int i; (i = next++) < (int)mine.size();) { int g = mine[i]; results[g] = fills[g]->run(q, i); }
             } catch (const std::exception& e) { std::lock_guard<std::mutex> l(emu); devErr[d] = e.what(); }
+            { timespec ts; clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts); cpuNs += (long long)ts.tv_sec * 1000000000LL + ts.tv_nsec; }
             q.workerExit();
         });
         for (auto& t : th) t.join();
-        fb_get_counters(ctx, &devCtr[d]); devTicks[d] = q.ticks();
+        devWork[d] = secs(d1, clk::now()); devCpu[d] = cpuNs.load() * 1e-9;
+        fb_get_counters(ctx, &devCtr[d]); devTicks[d] = q.ticks(); devEng[d] = q.engineSeconds(); devCopy[d] = q.copySeconds();
         fb_ctx_destroy(ctx);
     });
     for (auto& t : devThreads) t.join();
@@ -253,15 +267,15 @@ int fillgapsMain(int argc, const char* const* argv) {
     for (int d = 0; d < nD; d++) {
         rs.dev.placements_p1 += devCtr[d].placements_p1; rs.dev.placements_p2 += devCtr[d].placements_p2; rs.dev.base_terms += devCtr[d].base_terms;
         rs.dev.kernel_launches += devCtr[d].kernel_launches; rs.dev.device_ms = std::max(rs.dev.device_ms, devCtr[d].device_ms);
-        rs.dev.h2d_bytes += devCtr[d].h2d_bytes; rs.dev.d2h_bytes += devCtr[d].d2h_bytes; rs.ticks += devTicks[d];
+        rs.dev.h2d_bytes += devCtr[d].h2d_bytes; rs.dev.d2h_bytes += devCtr[d].d2h_bytes; rs.ticks += devTicks[d]; rs.tEngine = std::max(rs.tEngine, devEng[d]); rs.tCopy = std::max(rs.tCopy, devCopy[d]); rs.tCtx = std::max(rs.tCtx, devCtx[d]); rs.tWorkers = std::max(rs.tWorkers, devWork[d]); rs.cpuWorkers += devCpu[d];
     }
     if (const char* mp = getenv("FIGBIRD_METRICS")) {
         FILE* mf = fopen(mp, "w");
         if (mf) {
-            fprintf(mf, "{\"engine\": \"%s\", \"gaps\": %d, \"gpus\": %d, \"t_load\": %.6f, \"t_model\": %.6f, \"t_prepare\": %.6f, \"t_fill\": %.6f, \"t_write\": %.6f, "
+            fprintf(mf, "{\"engine\": \"%s\", \"gaps\": %d, \"gpus\": %d, \"t_load\": %.6f, \"t_model\": %.6f, \"t_prepare\": %.6f, \"t_fill\": %.6f, \"t_write\": %.6f, \"t_engine_calls\": %.6f, \"t_result_copy\": %.6f, \"t_ctx_upload\": %.6f, \"t_workers\": %.6f, \"cpu_workers\": %.6f, "
                         "\"ref_placements_p1\": %lld, \"dev_placements_p1\": %lld, \"dev_placements_p2\": %lld, \"dev_base_terms\": %lld, \"kernel_launches\": %lld, "
                         "\"device_ms\": %.6f, \"h2d_bytes\": %lld, \"d2h_bytes\": %lld, \"ticks\": %lld}\n",
-                    fb_engine_name(), nG, nD, rs.tLoad, rs.tModel, rs.tPrep, rs.tFill, rs.tWrite, (long long)rs.refPlacements, (long long)rs.dev.placements_p1,
+                    fb_engine_name(), nG, nD, rs.tLoad, rs.tModel, rs.tPrep, rs.tFill, rs.tWrite, rs.tEngine, rs.tCopy, rs.tCtx, rs.tWorkers, rs.cpuWorkers, (long long)rs.refPlacements, (long long)rs.dev.placements_p1,
                     (long long)rs.dev.placements_p2, (long long)rs.dev.base_terms, (long long)rs.dev.kernel_launches, rs.dev.device_ms, (long long)rs.dev.h2d_bytes,
                     (long long)rs.dev.d2h_bytes, (long long)rs.ticks);
             fclose(mf);

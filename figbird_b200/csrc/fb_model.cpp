@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <thread>
 
 #include "fb_host.h"
 
@@ -156,49 +157,94 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err) 
     for (char* p = text.data(); *p;) { lines.push_back(p); char* e = strchr(p, '\n'); if (!e) break; p = e + 1; }
     // NB: lines keep their '\n'; tokenisers treat it as a delimiter where the reference does.
 
-    std::vector<char> scratch(2048);
-    char mdKeep[1000]; mdKeep[0] = 0;
-    // ---- pass 1: processMapping
-    for (char* ln : lines) {
-        if (ln[0] == '@') continue;
+    // ---- pass 1: processMapping.  The statistics are integer counts, so the file is cut into blocks that are
+    // counted on separate threads and summed -- identical to the sequential result as long as every line carries its
+    // own MD/IH tags and no insert size hits the histogram-growth corner (Figbird.cpp:203); otherwise redo it serially.
+    auto pass1Line = [&](Stats& st, char* mdKeep, std::vector<char>& scratch, char* ln, bool& irregular) {
+        if (ln[0] == '@') return;
         size_t len = strcspn(ln, "\n"); if (len > 1022) len = 1022;   // fgets(1024)
         scratch.assign(ln, ln + len + 1); scratch[len] = '\n'; scratch.push_back(0);
         SamFields f;
-        if (!splitMyout(scratch.data(), f, mdKeep)) continue;
-        if (!(f.nh == 1 && mdKeep[5] != '^')) continue;
+        if (!splitMyout(scratch.data(), f, mdKeep)) { irregular = true; return; }
+        if (!f.haveMd || !f.haveNh) irregular = true;
+        if (!(f.nh == 1 && mdKeep[5] != '^')) return;
         long contigNo = atol(f.rname);
-        if (contigNo >= 0 && contigNo < (long)sc.seq.size() && (double)sc.seq[contigNo].size() > inputMean) bumpInsert(s, f.tlen);
+        if (contigNo >= 0 && contigNo < (long)sc.seq.size() && (double)sc.seq[contigNo].size() > inputMean) {
+            if (f.tlen >= st.maxInsertSize && f.tlen <= st.MAX_INSERT_SIZE) irregular = true;
+            bumpInsert(st, f.tlen);
+        }
         // processErrorTypes
         const int strand = (f.flag & 16) >> 4;
         int readLength = 0;
-        for (const char* c = f.seq; *c; c++, readLength++) s.baseCounts[baseIndex(*c)]++;
-        if (readLength < 1 || readLength > RL) continue;
-        s.readLengths[readLength - 1]++;
+        for (const char* c = f.seq; *c; c++, readLength++) st.baseCounts[baseIndex(*c)]++;
+        if (readLength < 1 || readLength > RL) { st.uniqueMappedReads++; return; }
+        st.readLengths[readLength - 1]++;
         std::vector<int> inserts(readLength, 0);
         int index = 0, curIndex = 0;
         walkCigar(f.cigar, "IDMS^\t\n ", [&](char op, int n) {
             if (op == 'M') { index += n; curIndex += n; }
             else if (op == 'I' || op == 'S') {
                 int at = strand == 0 ? index : readLength - index - 1;
-                if (at >= 0 && at < RL) s.inPos[at]++;
-                if (n >= 1 && n <= RL) s.inLengths[n - 1]++;
+                if (at >= 0 && at < RL) st.inPos[at]++;
+                if (n >= 1 && n <= RL) st.inLengths[n - 1]++;
                 if (curIndex >= 0 && curIndex < readLength) inserts[curIndex] = n;
                 index += n;
             } else if (op == 'D') {
                 int at = strand == 0 ? index : readLength - index - 1;
-                if (at >= 0 && at < RL) s.delPos[at]++;
-                if (n >= 1 && n <= RL) s.delLengths[n - 1]++;
+                if (at >= 0 && at < RL) st.delPos[at]++;
+                if (n >= 1 && n <= RL) st.delLengths[n - 1]++;
             }
         });
         walkMD(mdKeep, inserts, [&](char from, int idx, int cur) {
             int ri = idx - 1 + cur;
             char to = (ri >= 0 && ri < readLength) ? f.seq[ri] : 'N';
             int at = strand == 0 ? ri : readLength - idx - cur;
-            if (at >= 0 && at < RL) s.errorPos[at]++;
+            if (at >= 0 && at < RL) st.errorPos[at]++;
             int fi = baseIndex(from), ti = baseIndex(to);
-            if (fi != ti) s.errorTypes[fi][ti]++;
+            if (fi != ti) st.errorTypes[fi][ti]++;
         });
-        s.uniqueMappedReads++;
+        st.uniqueMappedReads++;
+    };
+    auto zeroStats = [&](Stats& z) {
+        z = s;
+        std::fill(z.insertCounts.begin(), z.insertCounts.end(), 0);
+        for (auto& r : z.errorTypes) for (auto& v : r) v = 0;
+        for (auto& v : z.baseCounts) v = 0;
+        for (auto* v : {&z.errorPos, &z.inPos, &z.inLengths, &z.delPos, &z.delLengths, &z.readLengths}) std::fill(v->begin(), v->end(), 0);
+        z.discardedReads = 0; z.uniqueMappedReads = 0;
+    };
+    int nThreads = (int)std::thread::hardware_concurrency();
+    if (const char* e = getenv("FIGBIRD_HOST_THREADS")) nThreads = atoi(e);
+    size_t blockLines = 20000;      // lines per thread below which threading does not pay (FIGBIRD_MODEL_BLOCK: tests force small blocks)
+    if (const char* e = getenv("FIGBIRD_MODEL_BLOCK")) blockLines = (size_t)std::max(1, atoi(e));
+    nThreads = std::max(1, std::min(nThreads, (int)(lines.size() / blockLines) + 1));
+    bool irregularAny = false;
+    if (nThreads > 1) {
+        std::vector<Stats> part(nThreads);
+        std::vector<char> irr(nThreads, 0);
+        std::vector<std::thread> th;
+        for (int t = 0; t < nThreads; t++) th.emplace_back([&, t] {
+            zeroStats(part[t]);
+            std::vector<char> scratch(2048); char mdKeep[1000]; mdKeep[0] = 0; bool ir = false;
+            const size_t lo = lines.size() * t / nThreads, hi = lines.size() * (t + 1) / nThreads;
+            for (size_t i = lo; i < hi; i++) pass1Line(part[t], mdKeep, scratch, lines[i], ir);
+            irr[t] = ir;
+        });
+        for (auto& t : th) t.join();
+        for (int t = 0; t < nThreads; t++) irregularAny |= (irr[t] != 0);
+        if (!irregularAny) {
+            for (int t = 0; t < nThreads; t++) {
+                const Stats& q = part[t];
+                for (size_t i = 0; i < s.insertCounts.size(); i++) s.insertCounts[i] += q.insertCounts[i];
+                for (int i = 0; i < 5; i++) { s.baseCounts[i] += q.baseCounts[i]; for (int j = 0; j < 5; j++) s.errorTypes[i][j] += q.errorTypes[i][j]; }
+                for (int i = 0; i < RL; i++) { s.errorPos[i] += q.errorPos[i]; s.inPos[i] += q.inPos[i]; s.inLengths[i] += q.inLengths[i]; s.delPos[i] += q.delPos[i]; s.delLengths[i] += q.delLengths[i]; s.readLengths[i] += q.readLengths[i]; }
+                s.discardedReads += q.discardedReads; s.uniqueMappedReads += q.uniqueMappedReads;
+            }
+        }
+    }
+    if (nThreads <= 1 || irregularAny) {
+        std::vector<char> scratch(2048); char mdKeep[1000]; mdKeep[0] = 0; bool ir = false;
+        for (char* ln : lines) pass1Line(s, mdKeep, scratch, ln, ir);
     }
 
     // ---- computeProbabilites (Figbird.cpp:497-844); only the quantities used downstream are kept
@@ -298,7 +344,7 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err) 
     };
 
     long gapProbs[1000] = {0};
-    {
+    if (nThreads <= 1 || irregularAny) {
         std::string pre1 = "*", pre2 = "*";
         long double tempProb = 0, gapProb = 0;
         char md1[1000], md2[1000]; md1[0] = md2[0] = 0;
@@ -332,6 +378,64 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err) 
                 tempProb = prob; gapProb = e2;
             } else { tempProb = prob; gapProb = e2; }
             pre1 = f1.qname; pre2 = f2.qname;
+        }
+    }
+    else {
+        // same histogram, pairs evaluated on threads (each pair's probabilities depend only on its two lines), then the
+        // sequential read-name grouping of Figbird.cpp:1290-1349 over the stored results
+        struct PairRes { const char* q1; const char* q2; int n1, n2; long double e2, prob; bool ok; };
+        std::vector<std::pair<char*, char*>> pairs;
+        for (size_t li = 0; li < lines.size();) {
+            char* l1 = lines[li++];
+            if (l1[0] == '@') continue;
+            if (li >= lines.size()) break;
+            pairs.emplace_back(l1, lines[li++]);
+        }
+        std::vector<PairRes> res(pairs.size());
+        std::vector<std::thread> th;
+        for (int t = 0; t < nThreads; t++) th.emplace_back([&, t] {
+            char md1[1000], md2[1000]; md1[0] = md2[0] = 0;
+            std::vector<char> b1(2048), b2(2048);
+            const size_t lo = pairs.size() * t / nThreads, hi = pairs.size() * (t + 1) / nThreads;
+            for (size_t i = lo; i < hi; i++) {
+                char* l1 = pairs[i].first; char* l2 = pairs[i].second;
+                size_t n1 = strcspn(l1, "\n"), n2 = strcspn(l2, "\n");
+                if (n1 > 1022) n1 = 1022;
+                if (n2 > 1022) n2 = 1022;
+                b1.assign(l1, l1 + n1 + 1); b1[n1] = '\n'; b1.push_back(0);
+                b2.assign(l2, l2 + n2 + 1); b2[n2] = '\n'; b2.push_back(0);
+                SamFields f1, f2;
+                PairRes& r = res[i];
+                r.ok = splitMyout(b1.data(), f1, md1) && splitMyout(b2.data(), f2, md2);
+                if (!r.ok) continue;
+                r.q1 = l1; r.n1 = (int)strlen(f1.qname); r.q2 = l2; r.n2 = (int)strlen(f2.qname);
+                int insertSize = std::max(f1.tlen, f2.tlen);
+                long double insertSizeProb = 0;
+                if (insertSize >= 0 && insertSize < MI) insertSizeProb = insertLengthDist[insertSize];
+                if (insertSizeProb == 0) insertSizeProb = 1 / (double)s.uniqueMappedReads;
+                long double e1 = errorProb(f1.cigar, md1, f1.seq, (f1.flag & 16) >> 4);
+                r.e2 = errorProb(f2.cigar, md2, f2.seq, (f2.flag & 16) >> 4);
+                long eff;
+                if (insertSize < 0) eff = totalContigLength;
+                else { eff = 0; for (auto& q : sc.seq) if ((long)q.size() >= insertSize) eff += ((long)q.size() - insertSize + 1); }
+                r.prob = (1 / (long double)(eff)) * insertSizeProb * e1 * r.e2;
+            }
+        });
+        for (auto& t : th) t.join();
+        const char* p1 = "*"; int pn1 = 1; const char* p2 = "*"; int pn2 = 1;
+        long double tempProb = 0, gapProb = 0;
+        auto same = [](const char* a, int an, const char* b, int bn) { return an == bn && memcmp(a, b, an) == 0; };
+        for (const PairRes& r : res) {
+            if (!r.ok) continue;
+            if (same(p1, pn1, r.q1, r.n1) && same(p2, pn2, r.q2, r.n2)) {
+                if (tempProb < r.prob) { tempProb = r.prob; gapProb = r.e2; }
+            } else if (!same(p1, pn1, "*", 1) && !same(p2, pn2, "*", 1)) {
+                int gapIndex = -std::log10(gapProb);
+                gapIndex++;
+                if (gapIndex < 1000 && gapIndex >= 0) gapProbs[gapIndex]++; else gapProbs[999]++;
+                tempProb = r.prob; gapProb = r.e2;
+            } else { tempProb = r.prob; gapProb = r.e2; }
+            p1 = r.q1; pn1 = r.n1; p2 = r.q2; pn2 = r.n2;
         }
     }
     {   // Figbird.cpp:7155-7178

@@ -52,3 +52,14 @@ def test_sharding_over_two_contexts_is_invariant(case):
     two = fc.run_ours(case, "unmapped", fc.oracle_exe(), extra_env={"FIGBIRD_GPUS": "0,1", "FIGBIRD_INFLIGHT": "2"}, name="two")
     for f in ("gapout.txt", "filledContigs.fa", "Ncount.txt", "draw.txt"):
         assert one[f] == two[f]
+
+
+@pytest.mark.parametrize("mode", ["partial", "unmapped"])
+def test_threaded_model_learning_is_identical(case, mode):
+    """learnModel cut into blocks on host threads (forced small blocks) gives the same tables and cut-offs as the
+    sequential parse, i.e. as the reference (Figbird.cpp:7118-7200)."""
+    model = os.path.join(case, "oracle_model_thr_%s.txt" % mode)
+    o = fc.run_ours(case, mode, fc.oracle_exe(), extra_env={"FIGBIRD_DUMP_MODEL": model, "FIGBIRD_HOST_THREADS": "5", "FIGBIRD_MODEL_BLOCK": "64"}, name="thr")
+    exp = gu.expected(case, mode)
+    assert o["gapout.txt"] == exp["gapout.txt"]
+    assert gu.model_lines(model) == gu.model_lines(os.path.join(case, "expected", mode, "model.txt"))
