@@ -1,29 +1,45 @@
-// fb_engine.cu -- the CUDA (sm_100a) engine behind include/figbird_b200.h.
+// fb_engine.cu -- the CUDA (sm_100a) engine behind include/figbird_b200.h (kernel revision 3).
 //
 // One CTA owns one work item = one (gap, candidate length) and runs the whole EM chain of that item on
 // chip: initialisation from the partial-read pile-ups, then per round pass 1 (weighted votes), soft
 // consensus, pass 2 (hard placement against the consensus), hard consensus / coverage, comp_count and the
-// M-step, with the row tables (P, E, counts) resident in shared memory.  Reference arithmetic:
+// M-step, with the row tables resident in shared memory.  Reference arithmetic:
 //   placeReads          Figbird.cpp:3022-4387     computeProbsGap / computeErrorProbsGap  :2090-2137
 //   computeSequence     Figbird.cpp:4417-4508     update_partial_prob (initial gap rows)   :1913-2088
 //
-// Numerics.  The filled sequence must equal the reference's, so every product is formed in the reference's
-// order with separately rounded IEEE operations (__dmul_rn/__dadd_rn/__ddiv_rn are never contracted to FMA;
-// x86-64 g++ emits none either).  Per-read maxima are returned as raw products so that the host applies
-// glibc's log/log10 exactly as the reference does; the accept test -log10(p) < cutoff is turned into
-// p >= accept_min_p with a threshold found by bisection on glibc's log10 at model upload.  Only the soft
-// weights (exp / pow of device logs) and the summation order of the votes differ from the CPU, at the
-// 1e-15 relative level; the vote reduction is a fixed-order gather, so results are run-to-run deterministic.
+// What bounds the path and how the kernel is shaped by it.  A pass-1 base term needs the row
+// entry {P[r][c], E[r][c]} (16 B) and the shared-memory crossbar moves 128 B/clk/SM, i.e. at most 8 terms per
+// clock and SM -- a quarter of what the FP64 pipe could multiply.  So the kernel spends crossbar bytes only on
+// terms that need them:
+//   * Flank rows never change (one-hot), so the product of a read's bases that land on the flanks depends
+//     only on (read, number of bases on that flank): fb_flank_kernel computes these once per gap batch
+//     (LF[q][a], RF[q][b]) and every candidate length and every EM round reuses them.
+//   * The gap-row terms of all placements of a read form the rectangle rows x read bases; placement x0 owns
+//     the diagonal row - j = x0.  A lane walks a diagonal class xi = x0 mod Lg with warp-uniform read base j
+//     over a table that is stored cyclically extended, so neighbouring lanes read neighbouring 16-byte
+//     entries (conflict-free LDS.128) and a lane that leaves the gap on the right continues with the
+//     placement that enters on the left: no lane idles on flank bases.  Per term: one LDS.128 of {P, E-P},
+//     one DFMA (P + e*(E-P)), one DMUL.
+//   * Only placements inside the admissible insert-size band of a read are stored or visited (the band is
+//     an interval in x0, computed once per item).
+//   * Pass 2 is exact (products of table entries in read order) but every factor is <= 1, so running
+//     products only fall: each read first evaluates the offset that won pass 1, and every other offset is
+//     dropped as soon as its running product is below that value.  Results are identical to the unpruned
+//     scan (first maximum, ties to the lowest offset).
 //
-// Mapping.  Pass 1/2 work unit = (read, 32 consecutive offsets): one warp, lane = offset, all lanes walk
-// the same read base j, so read codes and error-model entries are warp-uniform and table rows are
-// consecutive across lanes (conflict-free 8-byte shared loads).  Weights of a chunk of reads are parked in
-// shared memory (W), then gathered per gap row in fixed order into the count matrices -- no atomics on
-// doubles.  There is no CPU path in this file: without a device fb_ctx_create fails.
+// Numerics.  Pass-2 products, positions, accept tests, votes, consensus and coverage are bit-exact with the
+// CPU (separately rounded IEEE operations in the reference's order; the accept test -log10(p) < cutoff is
+// p >= accept_min_p with a threshold found by bisection on glibc's log10 at model upload).  Pass-1 products
+// are re-associated (flank product x gap product) and use P + e*(E-P): they agree with the reference to
+// ~1e-14 relative, far inside the 1e-5 bar on the base weights; every placement is still a fixed function
+// of its local inputs and the vote reduction is a fixed-order gather, so results are deterministic and
+// candidate lengths that see identical inputs get identical likelihoods, as in the reference.
+// There is no CPU path in this file: without a device fb_ctx_create fails.
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cfloat>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -37,9 +53,9 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxSmem = 200 * 1024;      // dynamic shared memory we opt in to (227 KB is the sm_100 limit)
-constexpr int kChunkWant = 40 * 1024;     // W + read-code staging we ask for per CTA when the reads allow it
+constexpr int kChunkWant = 32 * 1024;     // weights + read-code staging we ask for per CTA when the reads allow it
 constexpr int kNumBuckets = 4;
-__host__ __device__ constexpr int bucketCap(int b) { return b == 0 ? 28 * 1024 : b == 1 ? 56 * 1024 : b == 2 ? 100 * 1024 : kMaxSmem; }
+__host__ __device__ constexpr int bucketCap(int b) { return b == 0 ? 36 * 1024 : b == 1 ? 72 * 1024 : b == 2 ? 108 * 1024 : kMaxSmem; }
 
 struct DevGap { long long gap_start; int mode, orig_len, n_reads, read_begin, flank_len, flank_begin, pile_len, pile_begin; };
 
@@ -49,82 +65,100 @@ struct DevItem {
     long long counts_in_off, string_in_off;     // byte offsets into the input arena (-1: none)
     long long out_off;                           // byte offset of the FbItemOut header in the output arena
     long long scratch_off;                       // byte offset of this item's global table scratch (-1: tables in smem)
+    long long meta_off;                          // byte offset of this item's per-read metadata in the meta scratch
     long long off_p1, off_p2, off_pos, off_soft, off_hard, off_cov, off_counts;   // relative to out_off
 };
 
 struct DevModel {
-    const double* e; const double* ome; const double* match;   // [k]
+    const double* e; const double* match;   // [k]
     const double* pdf; int n_insert;
     double etp[25];
     int tmin, tmax, max_read_len;
+    int prunable;                           // every pass-2 factor is in [0, 1]: running products are monotone
     double accept_min_p;
 };
 
 struct Params {
     DevModel m;
     const DevGap* gaps;
-    const int* read_len; const long long* read_off; const int* read_mate;
+    const int* read_len; const long long* read_off; const int* read_mate; const int* read_gap;
     const unsigned char* read_flags; const unsigned char* read_jlo; const unsigned char* read_jcut; const unsigned char* codes;
     const unsigned char* flank; const int* pile_l; const int* pile_r;
+    double* lfrf;                   // per read: LF[len] then RF[len] at 2*read_off (fb_flank_kernel)
     const DevItem* items;
-    const unsigned char* in_arena; unsigned char* out_arena; unsigned char* scratch;
-    unsigned long long* counters;   // [0] pass-1 placements, [1] pass-2 placements, [2] base terms
+    const unsigned char* in_arena; unsigned char* out_arena; unsigned char* scratch; unsigned char* meta;
+    unsigned long long* counters;   // [0] pass-1 placements, [1] pass-2 placements, [2] base terms, [3] pass-1 lane steps, [4] pass-2 lane steps
 };
 
 // Shared-memory plan of one item, computed identically on host (sizing, bucketing) and device (carving).
 //   table region (shared memory, or a global scratch slice for very long candidates):
-//     UT[5][S] double2 {P,E}: slot f<5 = flank row of scaffold code f, slot 5+x = gap row x   (S = 5+Lg)
-//     C[5][Lg] countsGap, GP[split][5][Lg] gather partials, NC[5][Lg] new_counts_gap, RS[rows] slot of window row,
-//     G[rows] gapString codes, PREV[Lg] previous hard consensus
-//   local region (always shared): MT1[k]={1-e,e}, MT2[k]={1-e-ins-del,e}, ETP[25], then per chunk of reads RC (codes) and W.
-struct Plan { int S, rows, split, oUT, oC, oGP, oNC, oRS, oG, oPREV, tableBytes, oMT1, oMT2, oETP, localFixed, maxLenPad, strideP, perRead; };
+//     UT[5][S] double2 {P, E-P}: plane c = read base code, entry r = gap row r mod Lg for r < S = Lg + maxLenPad
+//     (cyclic extension, so that a lane's address is linear in the read base index),
+//     C[5][Lg] countsGap, GP[split][5][Lg] gather partials, NC[5][Lg] new_counts_gap, G[rows] gapString codes,
+//     PREV[Lg] previous hard consensus
+//   local region (always shared): ME[k] = e, MT2[k] = {1-e-ins-del, e}, ETP[25], then per chunk of reads RC (codes) and W.
+struct Plan { int S, rows, split, oUT, oC, oGP, oNC, oG, oPREV, tableBytes, oME, oMT2, oETP, localFixed, maxLenPad, nMax, perRead; };
 __host__ __device__ inline int al16(int x) { return (x + 15) & ~15; }
-__host__ __device__ inline Plan makePlan(int Lg, int F, int modelLen, int maxLen, int mode) {
+__host__ __device__ inline Plan makePlan(int Lg, int F, int modelLen, int maxLen, int mode, int bandMax) {
     Plan p;
-    p.S = 5 + Lg; p.rows = Lg + 2 * F;
+    p.maxLenPad = (maxLen + 15) & ~15;
+    p.S = Lg + p.maxLenPad; p.rows = Lg + 2 * F;
     p.split = (Lg >= 128 || Lg <= 0) ? 1 : (kThreads / Lg > 8 ? 8 : kThreads / Lg);
     int o = 0;
     p.oUT = o; o += 16 * 5 * p.S;
     p.oC = o; o += 8 * 5 * Lg;
     p.oGP = o; o += (p.split > 1) ? 8 * 5 * Lg * p.split : 0;
     p.oNC = o; o += 4 * 5 * Lg;
-    p.oRS = o; o += al16(2 * p.rows);
     p.oG = o; o += al16(p.rows);
     p.oPREV = o; o += al16(Lg);
     p.tableBytes = al16(o);
     o = 0;
-    p.oMT1 = o; o += 16 * modelLen;
+    p.oME = o; o += al16(8 * modelLen);
     p.oMT2 = o; o += 16 * modelLen;
     p.oETP = o; o += 208;
     p.localFixed = al16(o);
-    p.maxLenPad = (maxLen + 15) & ~15;
-    const int stride = (mode == FB_MODE_UNMAPPED) ? (maxLen + Lg - 1) : (maxLen - 1);
-    p.strideP = stride > 1 ? stride : 1;
-    p.perRead = 8 * p.strideP + p.maxLenPad;
+    int n = (mode == FB_MODE_UNMAPPED) ? (maxLen + Lg - 1) : (maxLen - 1);
+    if (mode == FB_MODE_UNMAPPED && bandMax < n) n = bandMax;     // unmapped reads always pass through the insert-size filter
+    p.nMax = n > 1 ? n : 1;
+    p.perRead = 8 * p.nMax + p.maxLenPad;
     return p;
 }
 
-__device__ __forceinline__ bool admissible(const DevModel& m, const DevGap& g, int fl, int rel, int len, int x0, int Lg, bool finalizeRef, int* tOut) {
-    const long long off = (long long)Lg - g.orig_len;
-    bool apply; long long t;
-    if (g.mode == FB_MODE_UNMAPPED) { apply = true; t = (fl & FB_READ_LEFT) ? ((long long)x0 - rel + len) : ((long long)rel + off + len - x0); }
-    else if (fl & FB_READ_LEFT) { apply = !(fl & FB_READ_NOMATE); t = (long long)x0 - rel + len; }
-    else {
-        long long absref;
-        if (fl & FB_READ_NOMATE) { if (!finalizeRef) { *tOut = 0; return true; } absref = -1 + off; }
-        else absref = (long long)rel + g.gap_start + off;
-        apply = (absref != -1);
-        t = (absref - g.gap_start) + len - x0;
-    }
-    *tOut = (int)t;
-    if (apply && (t < m.tmin || t > m.tmax)) return false;
-    return true;
+// Per-read metadata of one item (global scratch, written in the prologue): R+1 entries each.
+struct Meta { int* xlo; int* woff; int* u1; int* u2; int* x1; double* thr; };
+__host__ __device__ inline size_t metaBytes(int R) { return (size_t)al16(4 * (R + 1)) * 5 + (size_t)al16(8 * (R + 1)); }
+__device__ __forceinline__ Meta carveMeta(unsigned char* base, int R) {
+    Meta m; const size_t s = (size_t)al16(4 * (R + 1));
+    m.xlo = (int*)base; m.woff = (int*)(base + s); m.u1 = (int*)(base + 2 * s); m.u2 = (int*)(base + 3 * s); m.x1 = (int*)(base + 4 * s);
+    m.thr = (double*)(base + 5 * s);
+    return m;
 }
 
 __device__ __forceinline__ void window(const DevGap& g, int fl, int len, int Lg, int* lo, int* hi) {
     if (g.mode == FB_MODE_UNMAPPED) { *lo = -(len - 1); *hi = Lg - 1; }
     else if (fl & FB_READ_LEFT) { *lo = -(len - 1); *hi = -1; }
     else { *lo = Lg - len + 1; *hi = Lg - 1; }
+}
+
+// Admissible offsets of a read: window intersected with the insert-size filter (Figbird.cpp:3126-3135,3192-3203,
+// 3546-3554,3617-3624; finalize :5295).  The implied insert is linear in x0, so the set is an interval.
+__device__ __forceinline__ void band(const DevModel& m, const DevGap& g, int fl, int rel, int len, int Lg, bool finalizeRef, int* xlo, int* xhi) {
+    int lo, hi; window(g, fl, len, Lg, &lo, &hi);
+    const long long off = (long long)Lg - g.orig_len;
+    long long a = LLONG_MIN / 4, b = LLONG_MAX / 4;      // filter interval
+    if (g.mode == FB_MODE_UNMAPPED) {
+        if (fl & FB_READ_LEFT) { a = (long long)m.tmin + rel - len; b = (long long)m.tmax + rel - len; }          // t = x0 - rel + len
+        else { const long long A = (long long)rel + off + len; a = A - m.tmax; b = A - m.tmin; }                  // t = rel + off + len - x0
+    } else if (fl & FB_READ_LEFT) {
+        if (!(fl & FB_READ_NOMATE)) { a = (long long)m.tmin + rel - len; b = (long long)m.tmax + rel - len; }
+    } else {
+        bool apply = true; long long absref = 0;
+        if (fl & FB_READ_NOMATE) { if (!finalizeRef) apply = false; else absref = -1 + off; }
+        else absref = (long long)rel + g.gap_start + off;
+        if (apply && absref != -1) { const long long A = (absref - g.gap_start) + len; a = A - m.tmax; b = A - m.tmin; }   // t = A - x0
+    }
+    const long long l2 = a > lo ? a : lo, h2 = b < hi ? b : hi;
+    if (l2 > h2) { *xlo = lo; *xhi = lo - 1; } else { *xlo = (int)l2; *xhi = (int)h2; }
 }
 
 // E[j] = sum_{k<4, k!=j} P[k]*ETP[k][j] in k order (Figbird.cpp:2118-2137)
@@ -141,11 +175,67 @@ __device__ __forceinline__ void errRow(const double* etp, const double p[4], dou
 // soft weight of one placement (Figbird.cpp:3591,3601 unmapped; :3169,3179 partial)
 __device__ __forceinline__ double placementWeight(double p, bool unm) {
     if (unm) { const double s = log10(p); return exp(0.5 * s); }
-    // partial: w = pow(10, ln p).  These weights run down into the subnormal range and the reference's consensus still
-    // sees them (a row whose only vote is 4.9e-324 gets that base), so gradual underflow must round like glibc's pow:
-    // evaluate 300 decades higher (exact shift of the exponent argument) and let one IEEE multiply do the final scaling.
-    const double s = log(p);
-    return (s < -290.0) ? __dmul_rn(pow(10.0, s + 300.0), 1e-300) : pow(10.0, s);
+    // partial: w = pow(10, ln p) = exp(ln p * ln 10), the product formed in double-double so that the exponent
+    // argument carries no rounding of its own.  These weights run down into the subnormal range and the
+    // reference's consensus still sees them (a row whose only vote is 4.9e-324 gets that base), so gradual
+    // underflow must round like glibc's pow: evaluate 300 decades higher (exact shift of the exponent argument)
+    // and let one IEEE multiply do the final scaling.
+    double s = log(p);
+    const bool tiny = s < -290.0;
+    if (tiny) s += 300.0;
+    const double LN10_HI = 2.302585092994045901e+00, LN10_LO = -2.170756223382249351e-16;
+    const double ph = __dmul_rn(s, LN10_HI);
+    const double pl = __fma_rn(s, LN10_HI, -ph) + s * LN10_LO;
+    double w = exp(ph);
+    w = __fma_rn(w, pl, w);
+    return tiny ? __dmul_rn(w, 1e-300) : w;
+}
+
+// ---- flank products, once per gap batch.  One block per read.
+//   LF[a] = prod over scored bases j < a            of term(left flank base  lf[F - a + j], read base j)   (a bases on the left flank)
+//   RF[b] = prod over scored bases j >= len - b     of term(right flank base rf[j - (len - b)], read base j) (b bases on the right flank)
+// term for a one-hot (or all-N) row: P[c] + e[k]*(E[c] - P[c]) with the dense-row values of initialize + computeProbsGap.
+__global__ void __launch_bounds__(128) fb_flank_kernel(const Params prm, int nReads) {
+    __shared__ double sP[25], sD[25];
+    const int q = blockIdx.x;
+    if (q >= nReads) return;
+    const int tid = threadIdx.x;
+    if (tid < 25) {
+        const int f = tid / 5, c = tid % 5;
+        double p[4], e[5];
+#pragma unroll
+        for (int k = 0; k < 4; k++) p[k] = (f == 4) ? 0.25 : (f == k ? 1.0 : 0.0);
+        errRow(prm.m.etp, p, e);
+        const double P = (c < 4) ? p[c] : 0.0;
+        sP[tid] = P; sD[tid] = e[c] - P;
+    }
+    __syncthreads();
+    const int gi = prm.read_gap[q];
+    if (gi < 0) return;
+    const DevGap g = prm.gaps[gi];
+    const int len = prm.read_len[q], fl = prm.read_flags[q];
+    const int jlo = prm.read_jlo[q], jhi = len - prm.read_jcut[q];
+    const int F = g.flank_len;
+    const unsigned char* rc = prm.codes + prm.read_off[q];
+    const unsigned char* lf = prm.flank + g.flank_begin;
+    const unsigned char* rf = lf + F;
+    const bool rev = fl & FB_READ_REVERSE;
+    double* LF = prm.lfrf + 2 * prm.read_off[q];
+    double* RF = LF + len;
+    for (int a = tid; a < len; a += blockDim.x) {
+        double pl = 1.0, pr = 1.0;
+        const int je = jhi < a ? jhi : a;
+        for (int j = jlo; j < je; j++) {
+            const int f = lf[F - a + j], c = rc[j];
+            pl *= __fma_rn(prm.m.e[rev ? (len - 1 - j) : j], sD[f * 5 + c], sP[f * 5 + c]);
+        }
+        const int js = jlo > len - a ? jlo : len - a;
+        for (int j = js; j < jhi; j++) {
+            const int f = rf[j - (len - a)], c = rc[j];
+            pr *= __fma_rn(prm.m.e[rev ? (len - 1 - j) : j], sD[f * 5 + c], sP[f * 5 + c]);
+        }
+        LF[a] = pl; RF[a] = pr;
+    }
 }
 
 template <bool TSMEM>
@@ -155,12 +245,14 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
     const DevModel& m = prm.m;
     const int Lg = it.Lg, F = g.flank_len, R = g.n_reads;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const Plan pl = makePlan(Lg, F, m.max_read_len, it.max_len, g.mode);
-    const int S = pl.S, rows = pl.rows;
+    const bool unm = (g.mode == FB_MODE_UNMAPPED);
+    const Plan pl = makePlan(Lg, F, m.max_read_len, it.max_len, g.mode, m.tmax - m.tmin + 1);
+    const int S = pl.S, rows = pl.rows, mlp = pl.maxLenPad;
 
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ int s_comp, s_same, s_flags;
-    __shared__ unsigned long long s_place1, s_place2, s_terms;
+    __shared__ int s_comp, s_same, s_flags, s_q1;
+    __shared__ int s_scan[3][kThreads];
+    __shared__ unsigned long long s_lane1, s_lane2, s_terms;
 
     unsigned char* const tbase = TSMEM ? smem : (prm.scratch + it.scratch_off);
     unsigned char* const lbase = TSMEM ? smem + pl.tableBytes : smem;
@@ -168,20 +260,14 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
     double* const C = (double*)(tbase + pl.oC);
     double* const GP = (double*)(tbase + pl.oGP);
     int* const NC = (int*)(tbase + pl.oNC);
-    unsigned short* const RS = (unsigned short*)(tbase + pl.oRS);
     unsigned char* const G = tbase + pl.oG;
     unsigned char* const PREV = tbase + pl.oPREV;
-    double2* const MT1 = (double2*)(lbase + pl.oMT1);
+    double* const ME = (double*)(lbase + pl.oME);
     double2* const MT2 = (double2*)(lbase + pl.oMT2);
     double* const ETP = (double*)(lbase + pl.oETP);
     unsigned char* const chunkBase = lbase + pl.localFixed;
     const int chunkBytes = smemBytes - (TSMEM ? pl.tableBytes : 0) - pl.localFixed;
-    const int chunkReads = max(1, min(R > 0 ? R : 1, chunkBytes / pl.perRead));
-    unsigned char* const RC = chunkBase;                                    // [chunkReads][maxLenPad]
-    double* const W = (double*)(chunkBase + al16(chunkReads * pl.maxLenPad));   // [chunkReads][strideP]
-    const int strideP = pl.strideP, mlp = pl.maxLenPad;
-    const int cpr = (strideP + 63) / 64;     // 64-offset units per read (two offsets per lane)
-    const bool singleChunk = chunkReads >= R;
+    const Meta mt = carveMeta(prm.meta + it.meta_off, R);
 
     unsigned char* out = prm.out_arena + it.out_off;
     double* oP1 = (double*)(out + it.off_p1);
@@ -193,34 +279,63 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
 
     const unsigned char* lf = prm.flank + g.flank_begin;
     const unsigned char* rf = lf + F;
-    const bool unm = (g.mode == FB_MODE_UNMAPPED);
 
-    if (tid == 0) { s_comp = 0; s_flags = 0; s_place1 = 0; s_place2 = 0; s_terms = 0; }
-    // ---- model tables and window maps
-    for (int k = tid; k < m.max_read_len; k += kThreads) { MT1[k] = make_double2(m.ome[k], m.e[k]); MT2[k] = make_double2(m.match[k], m.e[k]); }
+    if (tid == 0) { s_comp = 0; s_flags = 0; s_lane1 = 0; s_lane2 = 0; s_terms = 0; }
+    // ---- model tables, flank part of the gap string
+    for (int k = tid; k < m.max_read_len; k += kThreads) { const double e = m.e[k]; ME[k] = e; MT2[k] = make_double2(m.match[k], e); }
     if (tid < 25) ETP[tid] = m.etp[tid];
     for (int r = tid; r < rows; r += kThreads) {
         const int x = r - F;
-        if (x >= 0 && x < Lg) RS[r] = (unsigned short)(5 + x);     // gap row (G[r] is written by the consensus / string_in)
-        else { const unsigned char c = (r < F) ? lf[r] : rf[r - F - Lg]; RS[r] = c; G[r] = c; }
+        if (x < 0 || x >= Lg) G[r] = (r < F) ? lf[r] : rf[r - F - Lg];     // gap part is written by the consensus / string_in
     }
+    __syncthreads();
+    // ---- per-read admissible band, prefix sums of band widths (W rows) and of pass-1 / pass-2 work units
+    const bool finRef = (it.kind == FB_ITEM_HARD) && (it.flags & FB_FLAG_FINALIZE_REF);
+    long long sumN = 0, sumTerms = 0;     // algorithmic placements / base terms of one placeReads call
+    {
+        const int per = max(1, (R + kThreads - 1) / kThreads);
+        const int qb = min(R, tid * per), qe = min(R, qb + per);
+        int sw = 0, s1 = 0, s2 = 0; long long st = 0;
+        for (int q = qb; q < qe; q++) {
+            const int qi = g.read_begin + q;
+            const int len = prm.read_len[qi];
+            int xlo, xhi; band(m, g, prm.read_flags[qi], prm.read_mate[qi], len, Lg, finRef, &xlo, &xhi);
+            const int n = xhi - xlo + 1;
+            mt.xlo[q] = xlo; mt.woff[q] = n;
+            sw += n; s1 += (Lg > 0) ? ((n < Lg ? n : Lg) + 31) / 32 : 0; s2 += (n + 63) / 64;
+            st += (long long)n * (len - prm.read_jcut[qi] - prm.read_jlo[qi]);
+        }
+        s_scan[0][tid] = sw; s_scan[1][tid] = s1; s_scan[2][tid] = s2;
+        if (st) atomicAdd(&s_terms, (unsigned long long)st);
+        __syncthreads();
+        if (tid < 3) { int acc = 0; for (int i = 0; i < kThreads; i++) { const int v = s_scan[tid][i]; s_scan[tid][i] = acc; acc += v; } }
+        __syncthreads();
+        sw = s_scan[0][tid]; s1 = s_scan[1][tid]; s2 = s_scan[2][tid];
+        for (int q = qb; q < qe; q++) {
+            const int n = mt.woff[q];
+            mt.woff[q] = sw; mt.u1[q] = s1; mt.u2[q] = s2;
+            sw += n; s1 += (Lg > 0) ? ((n < Lg ? n : Lg) + 31) / 32 : 0; s2 += (n + 63) / 64;
+        }
+        // entry R of each prefix array: written by the thread that owns the last read (thread 0 when R == 0)
+        const int lastOwner = (R > 0) ? (R - 1) / per : 0;
+        if (tid == lastOwner) { mt.woff[R] = sw; mt.u1[R] = s1; mt.u2[R] = s2; }
+        __syncthreads();
+        sumN = mt.woff[R];
+        sumTerms = (long long)s_terms;
+    }
+    const int totalW = (int)sumN;
+    const bool singleChunk = (8LL * totalW + (long long)R * mlp) <= (long long)chunkBytes;
     int prevValid = 0;   // previous hard consensus present (uniform)
 
-    auto storeRow = [&](int slot, const double p[4], const double e[5]) {
+    auto storeRow = [&](int x, const double p[4], const double e[5]) {     // gap row x and its cyclic copies
+        for (int r = x; r < S; r += Lg) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) UT[k * S + slot] = make_double2(p[k], e[k]);
-        UT[4 * S + slot] = make_double2(0.0, e[4]);     // read base N: term = e*E[4] == 0*(1-e) + e*E[4] exactly
+            for (int k = 0; k < 4; k++) UT[k * S + r] = make_double2(p[k], __dadd_rn(e[k], -p[k]));
+            UT[4 * S + r] = make_double2(0.0, e[4]);     // read base N: term = e*E[4]
+        }
     };
 
     if (it.kind == FB_ITEM_EM) {
-        // the five kinds of flank rows: one-hot counts (or 1 on N) -> P, E (initialize + computeProbsGap, Figbird.cpp:2342-2372, 2090-2109)
-        if (tid < 5) {
-            double p[4], e[5];
-#pragma unroll
-            for (int k = 0; k < 4; k++) p[k] = (tid == 4) ? 0.25 : (tid == k ? 1.0 : 0.0);
-            errRow(m.etp, p, e);
-            storeRow(tid, p, e);
-        }
         if (it.flags & FB_FLAG_RESUME) {
             const double* cin = (const double*)(prm.in_arena + it.counts_in_off);
             for (int i = tid; i < 5 * Lg; i += kThreads) { int x = i / 5, k = i % 5; C[k * Lg + x] = cin[i]; }
@@ -242,15 +357,16 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
 #pragma unroll
                 for (int k = 0; k < 4; k++) p[k] = __ddiv_rn(cnt[k], (double)tot);
                 errRow(m.etp, p, e);
-                storeRow(5 + x, p, e);
+                storeRow(x, p, e);
             }
         }
     } else {
         const unsigned char* sin = prm.in_arena + it.string_in_off;
         for (int x = tid; x < Lg; x += kThreads) { unsigned char c = it.string_in_off >= 0 ? sin[x] : 4; G[F + x] = c; oSoft[x] = c; oHard[x] = 4; oCov[x] = 0; }
-        for (int q = tid; q < R; q += kThreads) oP1[q] = -1.0;
+        for (int q = tid; q < R; q += kThreads) { oP1[q] = -1.0; mt.x1[q] = INT_MIN; }
     }
 
+    unsigned char* const RC = chunkBase;                                    // [reads in chunk][mlp]
     auto stageReads = [&](int q0, int q1) {   // read codes of the chunk -> RC
         const int n = (q1 - q0) * mlp;
         for (int i = tid; i < n; i += kThreads) {
@@ -258,6 +374,24 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
             const int qi = g.read_begin + q0 + ql;
             RC[i] = (j < prm.read_len[qi]) ? prm.codes[prm.read_off[qi] + j] : (unsigned char)4;
         }
+    };
+    // reads [q0, q1) whose codes + weight rows fit the chunk region (at least one read)
+    auto chunkEnd = [&](int q0) -> int {
+        if (singleChunk) return R;
+        __syncthreads();
+        if (tid == 0) {
+            int q = q0; long long bytes = 0;
+            while (q < R) { const long long nb = 8LL * (mt.woff[q + 1] - mt.woff[q]) + mlp; if (q > q0 && bytes + nb > chunkBytes) break; bytes += nb; q++; }
+            s_q1 = q;
+        }
+        __syncthreads();
+        return s_q1;
+    };
+    // read that owns work unit `target` in a prefix array (largest q in [q0, q1) with pre[q] <= target)
+    auto findRead = [&](const int* pre, int q0, int q1, int target) -> int {
+        int lo = q0, hi = q1 - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (pre[mid] <= target) lo = mid; else hi = mid - 1; }
+        return lo;
     };
     if (singleChunk) stageReads(0, R);
     __syncthreads();
@@ -276,64 +410,94 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
 #pragma unroll
             for (int k = 0; k < 4; k++) p[k] = (total != 0.0) ? __ddiv_rn(__dadd_rn(c[k], nq), total) : 0.25;
             errRow(m.etp, p, e);
-            storeRow(5 + x, p, e);
+            storeRow(x, p, e);
         }
     };
     if (it.kind == FB_ITEM_EM && (it.flags & FB_FLAG_RESUME)) { mstep(); __syncthreads(); }
 
     // ---- pass 2: products of exact table entries against the gap string, first maximum, accept, unit votes
-    auto pass2 = [&](int slot, bool finalizeRef, bool vote) {
-        for (int q0 = 0; q0 < R; q0 += chunkReads) {
-            const int q1 = min(R, q0 + chunkReads);
+    auto pass2 = [&](int slot, bool vote) {
+        for (int q0 = 0, q1; q0 < R; q0 = q1) {
+            q1 = chunkEnd(q0);
             if (!singleChunk) { stageReads(q0, q1); __syncthreads(); }
-            const int units = (q1 - q0) * cpr;
+            double* const W = (double*)(chunkBase + (size_t)(q1 - q0) * mlp);
+            const int wbase = mt.woff[q0], ubase = mt.u2[q0];
+            // exact product at the offset that won pass 1: every other offset only has to beat it
+            for (int ql = tid; ql < q1 - q0; ql += kThreads) {
+                const int q = q0 + ql, qi = g.read_begin + q;
+                const int x1 = mt.x1[q];
+                double thr = 0.0;
+                if (x1 != INT_MIN && m.prunable) {
+                    const int len = prm.read_len[qi], fl = prm.read_flags[qi];
+                    const int jlo = prm.read_jlo[qi], jhi = len - prm.read_jcut[qi];
+                    const bool rev = fl & FB_READ_REVERSE;
+                    const unsigned char* rc = RC + ql * mlp;
+                    const unsigned char* gs = G + F + x1;
+                    double p = 1.0;
+                    for (int j = jlo; j < jhi; j++) {
+                        const int c = rc[j], f = gs[j];
+                        const double2 mk = MT2[rev ? (len - j - 1) : j];
+                        p = __dmul_rn(p, (f == c) ? mk.x : __dmul_rn(mk.y, ETP[f * 5 + c]));
+                    }
+                    thr = p;
+                }
+                mt.thr[q] = thr;
+            }
+            __syncthreads();
+            const int units = mt.u2[q1] - ubase;
             for (int u = warp; u < units; u += kWarps) {
-                const int ql = u / cpr, ch = u - ql * cpr;
-                const int qi = g.read_begin + q0 + ql;
-                const int len = prm.read_len[qi], fl = prm.read_flags[qi], rel = prm.read_mate[qi];
+                const int q = findRead(mt.u2, q0, q1, u + ubase), ql = q - q0, qi = g.read_begin + q;
+                const int ch = u + ubase - mt.u2[q];
+                const int len = prm.read_len[qi], fl = prm.read_flags[qi];
                 const int jlo = prm.read_jlo[qi], jhi = len - prm.read_jcut[qi];
-                int lo, hi; window(g, fl, len, Lg, &lo, &hi);
+                const int xlo = mt.xlo[q], n = mt.woff[q + 1] - mt.woff[q];
+                const double thr = mt.thr[q];
+                const int x1 = (thr > 0.0) ? mt.x1[q] : INT_MIN;      // known exactly: not walked again
                 const int ia = ch * 64 + lane, ib = ia + 32;
-                const int xa = lo + ia, xb = lo + ib;
-                int ta, tb;
-                const bool acta = (xa <= hi) && admissible(m, g, fl, rel, len, xa, Lg, finalizeRef, &ta);
-                const bool actb = (xb <= hi) && admissible(m, g, fl, rel, len, xb, Lg, finalizeRef, &tb);
-                const unsigned ma = __ballot_sync(0xffffffffu, acta), mb = __ballot_sync(0xffffffffu, actb);
+                const int xa = xlo + ia, xb = xlo + ib;
+                const bool ina = ia < n, inb = ib < n;
+                bool acta = ina && xa != x1, actb = inb && xb != x1;
                 double pa = 1.0, pb = 1.0;
-                if (ma | mb) {
-                    const int ra = acta ? xa + F : (actb ? xb + F : F), rb = actb ? xb + F : ra;
+                if (__any_sync(0xffffffffu, acta || actb)) {
+                    const int ra = F + (ina ? xa : xlo), rb = F + (inb ? xb : (ina ? xa : xlo));
                     const bool rev = fl & FB_READ_REVERSE;
                     const unsigned char* rc = RC + ql * mlp;
                     const unsigned char* ga = G + ra; const unsigned char* gb = G + rb;
-#pragma unroll 2
-                    for (int j = jlo; j < jhi; j++) {
-                        const int c = rc[j];
-                        const double2 mk = MT2[rev ? (len - j - 1) : j];      // x = 1-e-ins-del, y = e
-                        const int fa = ga[j], fb = gb[j];
-                        const double va = (fa == c) ? mk.x : __dmul_rn(mk.y, ETP[fa * 5 + c]);
-                        const double vb = (fb == c) ? mk.x : __dmul_rn(mk.y, ETP[fb * 5 + c]);
-                        pa = __dmul_rn(pa, va); pb = __dmul_rn(pb, vb);
+                    int j = jlo, steps = 0;
+                    while (j < jhi) {
+                        const int je = min(jhi, j + 4);
+#pragma unroll 4
+                        for (; j < je; j++) {
+                            const int c = rc[j];
+                            const double2 mk = MT2[rev ? (len - j - 1) : j];      // x = 1-e-ins-del, y = e
+                            const int fa = ga[j], fb = gb[j];
+                            const double va = (fa == c) ? mk.x : __dmul_rn(mk.y, ETP[fa * 5 + c]);
+                            const double vb = (fb == c) ? mk.x : __dmul_rn(mk.y, ETP[fb * 5 + c]);
+                            pa = __dmul_rn(pa, va); pb = __dmul_rn(pb, vb);
+                        }
+                        steps += 4;
+                        if (!__any_sync(0xffffffffu, (acta && pa >= thr) || (actb && pb >= thr))) break;
                     }
-                    if (lane == 0) { const unsigned n = __popc(ma) + __popc(mb); atomicAdd(&s_place2, (unsigned long long)n); atomicAdd(&s_terms, (unsigned long long)n * (unsigned long long)(jhi - jlo)); }
+                    if (lane == 0) atomicAdd(&s_lane2, (unsigned long long)steps * 64ull);
                 }
-                if (ia < strideP) W[ql * strideP + ia] = acta ? pa : -1.0;
-                if (ib < strideP) W[ql * strideP + ib] = actb ? pb : -1.0;
+                if (ina) W[mt.woff[q] - wbase + ia] = acta ? pa : thr;
+                if (inb) W[mt.woff[q] - wbase + ib] = actb ? pb : thr;
             }
             __syncthreads();
             // first maximum over ascending offsets (strict >), accept test, unit votes (Figbird.cpp:3787-3912)
             for (int ql = warp; ql < q1 - q0; ql += kWarps) {
                 const int q = q0 + ql, qi = g.read_begin + q;
-                const int len = prm.read_len[qi], fl = prm.read_flags[qi];
-                int lo, hi; window(g, fl, len, Lg, &lo, &hi);
-                const int n = hi - lo + 1;
+                const int len = prm.read_len[qi];
+                const int xlo = mt.xlo[q], n = mt.woff[q + 1] - mt.woff[q];
+                const double* Wq = W + (mt.woff[q] - wbase);
                 double best = -1.0; int bestI = 0x7fffffff;
-                for (int i = lane; i < n; i += 32) { double v = W[ql * strideP + i]; if (v > best) { best = v; bestI = i; } }
+                for (int i = lane; i < n; i += 32) { double v = Wq[i]; if (v > best) { best = v; bestI = i; } }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     double ov = __shfl_xor_sync(0xffffffffu, best, o); int oi = __shfl_xor_sync(0xffffffffu, bestI, o);
                     if (ov > best || (ov == best && oi < bestI)) { best = ov; bestI = oi; }
                 }
-                const int bestx = (best >= 0) ? lo + bestI : 0;
+                const int bestx = (best >= 0) ? xlo + bestI : 0;
                 if (lane == 0) { oP2[(size_t)slot * R + q] = best; oPos[(size_t)slot * R + q] = bestx; }
                 if (vote && unm && best >= m.accept_min_p) {
                     const unsigned char* rc = RC + ql * mlp;
@@ -353,82 +517,122 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
 
     int calls = 0;
     if (it.kind == FB_ITEM_HARD) {
-        pass2(0, (it.flags & FB_FLAG_FINALIZE_REF) != 0, false);
+        pass2(0, false);
         calls = 1;
     } else {
         const int maxCalls = it.max_rounds + ((it.flags & FB_FLAG_EXTRA_PASS) ? 1 : 0);
         bool emDone = it.max_rounds <= 0;
         const int split = pl.split;
+        const long long offLg = (long long)Lg - g.orig_len;
         for (int call = 0; call < maxCalls; call++) {
             const bool extra = emDone;
             const int slot = (it.flags & FB_FLAG_RECORD_ALL) ? call : 0;
             for (int i = tid; i < 5 * Lg; i += kThreads) { C[i] = 0.0; NC[i] = 0; }
-            for (int q = tid; q < R; q += kThreads) oP1[(size_t)slot * R + q] = 0.0;   // bit pattern 0 == "no admissible offset yet"
             __syncthreads();
             // ================= pass 1 (Figbird.cpp:3082-3263, 3530-3689) =================
-            for (int q0 = 0; q0 < R; q0 += chunkReads) {
-                const int q1 = min(R, q0 + chunkReads);
+            for (int q0 = 0, q1; q0 < R; q0 = q1) {
+                q1 = chunkEnd(q0);
                 if (!singleChunk) { stageReads(q0, q1); __syncthreads(); }
-                const int units = (q1 - q0) * cpr;
+                double* const W = (double*)(chunkBase + (size_t)(q1 - q0) * mlp);
+                const int wbase = mt.woff[q0], ubase = mt.u1[q0];
+                // ---- gap-row products of every admissible placement: cyclic diagonal walk
+                const int units = (Lg > 0) ? mt.u1[q1] - ubase : 0;
                 for (int u = warp; u < units; u += kWarps) {
-                    const int ql = u / cpr, ch = u - ql * cpr;
-                    const int qi = g.read_begin + q0 + ql;
-                    const int len = prm.read_len[qi], fl = prm.read_flags[qi], rel = prm.read_mate[qi];
+                    const int q = findRead(mt.u1, q0, q1, u + ubase), ql = q - q0, qi = g.read_begin + q;
+                    const int uu = u + ubase - mt.u1[q];
+                    const int len = prm.read_len[qi], fl = prm.read_flags[qi];
                     const int jlo = prm.read_jlo[qi], jhi = len - prm.read_jcut[qi];
-                    int lo, hi; window(g, fl, len, Lg, &lo, &hi);
-                    const int ia = ch * 64 + lane, ib = ia + 32;
-                    const int xa = lo + ia, xb = lo + ib;
-                    int ta = 0, tb = 0;
-                    const bool acta = (xa <= hi) && admissible(m, g, fl, rel, len, xa, Lg, false, &ta);
-                    const bool actb = (xb <= hi) && admissible(m, g, fl, rel, len, xb, Lg, false, &tb);
-                    const unsigned ma = __ballot_sync(0xffffffffu, acta), mb = __ballot_sync(0xffffffffu, actb);
-                    double wa = 0.0, wb = 0.0, pa = 0.0, pb = 0.0;
-                    if (ma | mb) {
-                        const int ra = acta ? xa + F : (actb ? xb + F : F), rb = actb ? xb + F : ra;
-                        pa = (unm && acta) ? m.pdf[min(max(ta, 0), m.n_insert - 1)] : 1.0;
-                        pb = (unm && actb) ? m.pdf[min(max(tb, 0), m.n_insert - 1)] : 1.0;
-                        const bool rev = fl & FB_READ_REVERSE;
-                        const unsigned char* rc = RC + ql * mlp;
-                        const unsigned short* sa = RS + ra; const unsigned short* sb = RS + rb;
-#pragma unroll 2
-                        for (int j = jlo; j < jhi; j++) {
-                            const int cb = rc[j] * S;
-                            const double2 mk = MT1[rev ? (len - 1 - j) : j];      // x = 1-e, y = e
-                            const double2 va = UT[cb + sa[j]];
-                            const double2 vb = UT[cb + sb[j]];
-                            pa = __dmul_rn(pa, __dadd_rn(__dmul_rn(va.x, mk.x), __dmul_rn(mk.y, va.y)));
-                            pb = __dmul_rn(pb, __dadd_rn(__dmul_rn(vb.x, mk.x), __dmul_rn(mk.y, vb.y)));
+                    const int xlo = mt.xlo[q], n = mt.woff[q + 1] - mt.woff[q];
+                    double* const Wq = W + (mt.woff[q] - wbase);
+                    const bool full = n >= Lg;
+                    const int nl = full ? Lg : n;
+                    const int idx = uu * 32 + lane;
+                    const bool active = idx < nl;
+                    int js, je;
+                    if (full) { js = jlo; je = jhi; }
+                    else { const int xf = xlo + uu * 32, xl = min(xf + 31, xlo + n - 1); js = max(jlo, -xl); je = min(jhi, Lg - xf); }
+                    if (je <= js) continue;
+                    const int xi = active ? (full ? idx : xlo + idx) : (full ? 0 : xlo);
+                    int xm = xi % Lg; if (xm < 0) xm += Lg;
+                    const int m0 = (xm + js) / Lg;
+                    int x0cur = xm - m0 * Lg;          // placement whose segment contains read base js
+                    int jw = (m0 + 1) * Lg - xm;       // read base at which the walk re-enters gap row 0
+                    const double2* ptr = UT + xm;      // + j: cyclically extended table, plane 0
+                    const unsigned char* rc = RC + ql * mlp;
+                    const double* me = ME; int kstep = 1, kb = 0;
+                    if (fl & FB_READ_REVERSE) { kb = len - 1; kstep = -1; }
+                    double acc = 1.0;
+                    auto stepv = [&](int j, const double2 v, double e) {
+                        if (j == jw) {      // the walk re-enters gap row 0: the running product belongs to placement x0cur
+                            if (active && (unsigned)(x0cur - xlo) < (unsigned)n) Wq[x0cur - xlo] = acc;
+                            acc = 1.0; x0cur -= Lg; jw += Lg;
                         }
-                        if (acta && pa > 0.0) wa = placementWeight(pa, unm); else pa = 0.0;
-                        if (actb && pb > 0.0) wb = placementWeight(pb, unm); else pb = 0.0;
-                        // per-read maximum of the raw product (positive doubles order like their bit patterns)
-                        double pm = fmax(pa, pb);
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) pm = fmax(pm, __shfl_xor_sync(0xffffffffu, pm, o));
-                        if (lane == 0) {
-                            if (pm > 0.0) atomicMax((unsigned long long*)&oP1[(size_t)slot * R + q0 + ql], (unsigned long long)__double_as_longlong(pm));
-                            const unsigned n = __popc(ma) + __popc(mb);
-                            atomicAdd(&s_place1, (unsigned long long)n);
-                            atomicAdd(&s_terms, (unsigned long long)n * (unsigned long long)(jhi - jlo));
-                        }
+                        acc = __dmul_rn(acc, __fma_rn(e, v.y, v.x));
+                    };
+                    int j = js;
+                    for (; j < je && (j & 3); j++) stepv(j, ptr[rc[j] * S + j], me[kb + kstep * j]);
+                    for (; j + 4 <= je; j += 4) {
+                        const unsigned cw = *(const unsigned*)(rc + j);
+                        const double2* pj = ptr + j;
+                        const double2 v0 = pj[(cw & 0xff) * S], v1 = pj[((cw >> 8) & 0xff) * S + 1], v2 = pj[((cw >> 16) & 0xff) * S + 2], v3 = pj[(cw >> 24) * S + 3];
+                        const double e0 = me[kb + kstep * j], e1 = me[kb + kstep * (j + 1)], e2 = me[kb + kstep * (j + 2)], e3 = me[kb + kstep * (j + 3)];
+                        stepv(j, v0, e0); stepv(j + 1, v1, e1); stepv(j + 2, v2, e2); stepv(j + 3, v3, e3);
                     }
-                    if (ia < strideP) W[ql * strideP + ia] = wa;
-                    if (ib < strideP) W[ql * strideP + ib] = wb;
+                    for (; j < je; j++) stepv(j, ptr[rc[j] * S + j], me[kb + kstep * j]);
+                    if (active && (unsigned)(x0cur - xlo) < (unsigned)n) Wq[x0cur - xlo] = acc;
+                    if (lane == 0) atomicAdd(&s_lane1, (unsigned long long)(je - js) * 32ull);
                 }
                 __syncthreads();
-                // gather the weights of this chunk into the gap rows in a fixed order (deterministic, no FP atomics):
+                // ---- finish every placement: insert pdf x left-flank product x gap product x right-flank product,
+                //      per-read maximum (value and offset), soft weight in place
+                for (int ql = warp; ql < q1 - q0; ql += kWarps) {
+                    const int q = q0 + ql, qi = g.read_begin + q;
+                    const int len = prm.read_len[qi], fl = prm.read_flags[qi], rel = prm.read_mate[qi];
+                    const int jlo = prm.read_jlo[qi], jhi = len - prm.read_jcut[qi];
+                    const int xlo = mt.xlo[q], n = mt.woff[q + 1] - mt.woff[q];
+                    double* const Wq = W + (mt.woff[q] - wbase);
+                    const double* LF = prm.lfrf + 2 * prm.read_off[qi];
+                    const double* RF = LF + len;
+                    double best = 0.0; int bestI = 0x7fffffff;
+                    for (int i = lane; i < n; i += 32) {
+                        const int x0 = xlo + i;
+                        double p = 1.0;
+                        if (unm) {
+                            const long long t = (fl & FB_READ_LEFT) ? ((long long)x0 - rel + len) : ((long long)rel + offLg + len - x0);
+                            p = m.pdf[min(max((int)t, 0), m.n_insert - 1)];
+                        }
+                        if (x0 < 0) p = __dmul_rn(p, LF[-x0]);
+                        if (min(jhi, Lg - x0) > max(jlo, -x0)) p = __dmul_rn(p, Wq[i]);
+                        const int b = x0 + len - Lg;
+                        if (b > 0) p = __dmul_rn(p, RF[b]);
+                        double w = 0.0;
+                        if (p > 0.0) w = placementWeight(p, unm); else p = 0.0;
+                        Wq[i] = w;
+                        if (p > best) { best = p; bestI = i; }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        double ov = __shfl_xor_sync(0xffffffffu, best, o); int oi = __shfl_xor_sync(0xffffffffu, bestI, o);
+                        if (ov > best || (ov == best && oi < bestI)) { best = ov; bestI = oi; }
+                    }
+                    if (lane == 0) { oP1[(size_t)slot * R + q] = (best > 0.0) ? best : -1.0; mt.x1[q] = (best > 0.0) ? xlo + bestI : INT_MIN; }
+                }
+                __syncthreads();
+                // ---- gather the weights of this chunk into the gap rows in a fixed order (deterministic, no FP atomics):
                 // thread (row x, part s) sums reads s, s+split, ... ascending, read base ascending; parts are added in order.
                 for (int idx = tid; idx < Lg * split; idx += kThreads) {
                     const int s = idx / Lg, x = idx - s * Lg;
                     double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
                     for (int ql = s; ql < q1 - q0; ql += split) {
-                        const int qi = g.read_begin + q0 + ql;
-                        const int len = prm.read_len[qi], fl = prm.read_flags[qi];
+                        const int q = q0 + ql, qi = g.read_begin + q;
+                        const int n = mt.woff[q + 1] - mt.woff[q];
+                        if (n <= 0) continue;
+                        const int len = prm.read_len[qi];
+                        const int xlo = mt.xlo[q], xhi = xlo + n - 1;
                         const unsigned char* rc = RC + ql * mlp;
-                        int lo, hi; window(g, fl, len, Lg, &lo, &hi);
-                        // x0 = x - j in [lo, hi]  <=>  j in [x - hi, x - lo]
-                        const int ja = max(0, x - hi), jb = min(len - 1, x - lo);
-                        const double* wr = W + ql * strideP - lo;
+                        // x0 = x - j in [xlo, xhi]  <=>  j in [x - xhi, x - xlo]
+                        const int ja = max(0, x - xhi), jb = min(len - 1, x - xlo);
+                        const double* wr = W + (mt.woff[q] - wbase) - xlo;
                         for (int j = ja; j <= jb; j++) {
                             const double w = wr[x - j];
                             switch (rc[j]) { case 0: a0 = __dadd_rn(a0, w); break; case 1: a1 = __dadd_rn(a1, w); break; case 2: a2 = __dadd_rn(a2, w); break; case 3: a3 = __dadd_rn(a3, w); break; default: a4 = __dadd_rn(a4, w); }
@@ -452,8 +656,6 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
                 }
                 __syncthreads();
             }
-            // pass-1 maxima: bit pattern 0 means no admissible offset -> -1 (the atomics live in L2: bypass L1)
-            for (int q = tid; q < R; q += kThreads) { double v = __ldcg(&oP1[(size_t)slot * R + q]); if (!(v > 0.0)) oP1[(size_t)slot * R + q] = -1.0; }
             // ================= computeSequence(0,0) =================
             for (int x = tid; x < Lg; x += kThreads) {
                 double mx = 0; int mi = -1;
@@ -464,7 +666,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
             }
             __syncthreads();
             // ================= pass 2 =================
-            pass2(slot, false, true);
+            pass2(slot, true);
             // ================= computeSequence(1,1) + comp_count (Figbird.cpp:3916-3927) =================
             if (unm) {
                 if (tid == 0) s_same = 1;
@@ -506,8 +708,11 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
     __syncthreads();
     if (tid == 0) {
         FbItemOut* H = (FbItemOut*)out;
-        H->calls = calls; H->comp_count = s_comp; H->flags = s_flags; H->placements = (long long)s_place1;
-        atomicAdd(&prm.counters[0], s_place1); atomicAdd(&prm.counters[1], s_place2); atomicAdd(&prm.counters[2], s_terms);
+        const long long p1calls = (it.kind == FB_ITEM_HARD) ? 0 : calls;
+        H->calls = calls; H->comp_count = s_comp; H->flags = s_flags; H->placements = sumN * p1calls;
+        atomicAdd(&prm.counters[0], (unsigned long long)(sumN * p1calls)); atomicAdd(&prm.counters[1], (unsigned long long)(sumN * calls));
+        atomicAdd(&prm.counters[2], (unsigned long long)(sumTerms * (p1calls + calls)));
+        atomicAdd(&prm.counters[3], s_lane1); atomicAdd(&prm.counters[4], s_lane2);
     }
 }
 
@@ -543,11 +748,12 @@ struct fb_ctx {
     int smemOptin = 0;
     bool haveModel = false, haveBatch = false;
     DevModel dm{};
-    DevBuf<double> d_e, d_ome, d_match, d_pdf;
+    DevBuf<double> d_e, d_match, d_pdf, d_lfrf;
     std::vector<DevGap> hGaps; std::vector<int> hGapMaxLen;
-    DevBuf<DevGap> d_gaps; DevBuf<int> d_rlen, d_rmate, d_pl, d_pr; DevBuf<long long> d_roff;
+    DevBuf<DevGap> d_gaps; DevBuf<int> d_rlen, d_rmate, d_rgap, d_pl, d_pr; DevBuf<long long> d_roff;
     DevBuf<unsigned char> d_rfl, d_jlo, d_jcut, d_codes, d_flank;
-    DevBuf<DevItem> d_items; DevBuf<unsigned char> d_in, d_out, d_scratch;
+    DevBuf<DevItem> d_items; DevBuf<unsigned char> d_in, d_out, d_scratch, d_meta;
+    int nReads = 0; bool flankDirty = true;        // LF/RF products must be (re)computed before the next fb_em_run
     DevBuf<unsigned long long> d_ctr;
     unsigned char* h_out = nullptr; size_t h_out_cap = 0;     // pinned result arena
     unsigned char* h_in = nullptr; size_t h_in_cap = 0;       // pinned staging for items + inputs
@@ -574,7 +780,7 @@ extern "C" fb_status fb_ctx_create(int32_t device, fb_ctx** out) {
     CK(cudaFuncSetAttribute(fb_em_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     CK(cudaFuncSetAttribute(fb_em_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     for (int b = 0; b <= kNumBuckets; b++) { CK(cudaStreamCreateWithFlags(&c->bstream[b], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->bev[b], cudaEventDisableTiming)); }
-    CK(c->d_ctr.ensure(4)); CK(cudaMemset(c->d_ctr.p, 0, 4 * sizeof(unsigned long long)));
+    CK(c->d_ctr.ensure(8)); CK(cudaMemset(c->d_ctr.p, 0, 8 * sizeof(unsigned long long)));
     return FB_OK;
 }
 
@@ -582,7 +788,7 @@ extern "C" void fb_ctx_destroy(fb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    c->d_e.release(); c->d_ome.release(); c->d_match.release(); c->d_pdf.release();
+    c->d_e.release(); c->d_match.release(); c->d_pdf.release(); c->d_lfrf.release(); c->d_rgap.release(); c->d_meta.release();
     c->d_gaps.release(); c->d_rlen.release(); c->d_rmate.release(); c->d_pl.release(); c->d_pr.release(); c->d_roff.release();
     c->d_rfl.release(); c->d_jlo.release(); c->d_jcut.release(); c->d_codes.release(); c->d_flank.release();
     c->d_items.release(); c->d_in.release(); c->d_out.release(); c->d_scratch.release(); c->d_ctr.release();
@@ -605,20 +811,21 @@ extern "C" fb_status fb_model_upload(fb_ctx* c, const FbModel* m) {
     if (!c || !m || m->max_read_len <= 0 || m->n_insert <= 0) return FB_ERR_ARG;
     CK(cudaSetDevice(c->device));
     const int RL = m->max_read_len;
-    std::vector<double> ome(RL), match(RL);
+    std::vector<double> match(RL);
+    bool prunable = true;      // every pass-2 factor in [0, 1] => running products only fall (pass-2 pruning is exact)
     for (int k = 0; k < RL; k++) {
-        ome[k] = 1 - m->err_pos[k];
         match[k] = 1 - m->err_pos[k] - m->ins_pos[k] - m->del_pos[k];                 // Figbird.cpp:3400
+        if (!(match[k] >= 0.0 && match[k] <= 1.0 && m->err_pos[k] >= 0.0 && m->err_pos[k] <= 1.0)) prunable = false;
     }
+    for (int i = 0; i < 25; i++) if (!(m->err_type[i] >= 0.0 && m->err_type[i] <= 1.0)) prunable = false;
     fb_status s;
     if ((s = upload(c, c->d_e, m->err_pos, RL))) return s;
-    if ((s = upload(c, c->d_ome, ome.data(), RL))) return s;
     if ((s = upload(c, c->d_match, match.data(), RL))) return s;
     if ((s = upload(c, c->d_pdf, m->insert_pdf, m->n_insert))) return s;
     CK(cudaStreamSynchronize(c->stream));
-    c->dm.e = c->d_e.p; c->dm.ome = c->d_ome.p; c->dm.match = c->d_match.p; c->dm.pdf = c->d_pdf.p; c->dm.n_insert = m->n_insert;
+    c->dm.e = c->d_e.p; c->dm.match = c->d_match.p; c->dm.pdf = c->d_pdf.p; c->dm.n_insert = m->n_insert;
     memcpy(c->dm.etp, m->err_type, sizeof c->dm.etp);
-    c->dm.tmin = m->insert_min; c->dm.tmax = m->insert_max; c->dm.max_read_len = RL;
+    c->dm.tmin = m->insert_min; c->dm.tmax = m->insert_max; c->dm.max_read_len = RL; c->dm.prunable = prunable ? 1 : 0;
     // accept iff -log10(p) < cutoff (Figbird.cpp:3474,3852).  log10 is monotone, so the accepted set is
     // {p >= T}; find T = the smallest double glibc accepts, by bisection on the bit pattern.
     {
@@ -635,7 +842,7 @@ extern "C" fb_status fb_model_upload(fb_ctx* c, const FbModel* m) {
         }
         if (m->prob_cutoff <= 0) c->dm.accept_min_p = INFINITY;   // -log10(p) < 0 needs p > 1: never for a probability
     }
-    c->haveModel = true;
+    c->haveModel = true; c->flankDirty = true;
     return FB_OK;
 }
 
@@ -643,6 +850,7 @@ extern "C" fb_status fb_batch_upload(fb_ctx* c, const FbGapBatch* b) {
     if (!c || !b || b->n_gaps < 0) return FB_ERR_ARG;
     CK(cudaSetDevice(c->device));
     c->hGaps.resize(b->n_gaps); c->hGapMaxLen.assign(b->n_gaps, 1);
+    std::vector<int> readGap((size_t)std::max(b->n_reads, 1), -1);
     for (int i = 0; i < b->n_gaps; i++) {
         const FbGap& g = b->gaps[i];
         DevGap d{}; d.gap_start = g.gap_start; d.mode = g.mode; d.orig_len = g.orig_len; d.n_reads = g.n_reads; d.read_begin = g.read_begin;
@@ -650,7 +858,10 @@ extern "C" fb_status fb_batch_upload(fb_ctx* c, const FbGapBatch* b) {
         c->hGaps[i] = d;
         int ml = 1;
         for (int q = 0; q < g.n_reads; q++) {
+            if (g.read_begin + q < 0 || g.read_begin + q >= b->n_reads) { c->err = "read index out of range"; return FB_ERR_ARG; }
             int len = b->read_len[g.read_begin + q];
+            if (b->read_code_off[g.read_begin + q] < 0 || b->read_code_off[g.read_begin + q] + len > b->n_codes) { c->err = "read codes out of range"; return FB_ERR_ARG; }
+            readGap[g.read_begin + q] = i;
             if (len > g.flank_len + 1) { c->err = "flank_len must be >= read length - 1"; return FB_ERR_ARG; }
             if (len > 255) { c->err = "read longer than 255 bases"; return FB_ERR_ARG; }
             ml = len > ml ? len : ml;
@@ -661,6 +872,9 @@ extern "C" fb_status fb_batch_upload(fb_ctx* c, const FbGapBatch* b) {
     if ((s = upload(c, c->d_gaps, c->hGaps.data(), c->hGaps.size()))) return s;
     if ((s = upload(c, c->d_rlen, b->read_len, (size_t)b->n_reads))) return s;
     if ((s = upload(c, c->d_rmate, b->read_mate, (size_t)b->n_reads))) return s;
+    if ((s = upload(c, c->d_rgap, readGap.data(), (size_t)b->n_reads))) return s;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(c->d_lfrf.ensure(2 * (size_t)std::max<int64_t>(b->n_codes, 1)));
     { std::vector<long long> ro(b->read_code_off, b->read_code_off + b->n_reads); if ((s = upload(c, c->d_roff, ro.data(), ro.size()))) return s; CK(cudaStreamSynchronize(c->stream)); }
     if ((s = upload(c, c->d_rfl, b->read_flags, (size_t)b->n_reads))) return s;
     if ((s = upload(c, c->d_jlo, b->read_jlo, (size_t)b->n_reads))) return s;
@@ -670,7 +884,7 @@ extern "C" fb_status fb_batch_upload(fb_ctx* c, const FbGapBatch* b) {
     if ((s = upload(c, c->d_pl, b->pile_left, (size_t)b->n_pile_rows * 4))) return s;
     if ((s = upload(c, c->d_pr, b->pile_right, (size_t)b->n_pile_rows * 4))) return s;
     CK(cudaStreamSynchronize(c->stream));
-    c->haveBatch = true;
+    c->nReads = b->n_reads; c->haveBatch = true; c->flankDirty = true;
     return FB_OK;
 }
 
@@ -687,7 +901,8 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
     CK(cudaSetDevice(c->device));
     auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
     std::vector<DevItem> di(n);
-    size_t outTotal = 0, inTotal = 0, scratchTotal = 0;
+    size_t outTotal = 0, inTotal = 0, scratchTotal = 0, metaTotal = 0;
+    const int bandMax = c->dm.tmax - c->dm.tmin + 1;
     std::vector<int> bucketOf(n, 0);
     int bucketSmem[kNumBuckets + 1] = {0, 0, 0, 0, 0};
     int bucketCount[kNumBuckets + 1] = {0, 0, 0, 0, 0};
@@ -720,7 +935,8 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
         // shared-memory plan: tables + model + at least one read's chunk must fit, else tables go to global scratch
         const int ml = c->hGapMaxLen[it.gap];
         d.max_len = ml;
-        const Plan pl = makePlan(Lg, g.flank_len, c->dm.max_read_len, ml, g.mode);
+        d.meta_off = (long long)metaTotal; metaTotal += metaBytes(R);
+        const Plan pl = makePlan(Lg, g.flank_len, c->dm.max_read_len, ml, g.mode, bandMax);
         const long long want = std::min<long long>((long long)pl.perRead * std::max(R, 1), kChunkWant);
         const long long chunk = std::max<long long>(want, pl.perRead) + 32;
         if ((long long)pl.tableBytes + pl.localFixed + pl.perRead + 32 <= kMaxSmem) {
@@ -769,6 +985,7 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
     CK(c->d_in.ensure(inBytes));
     CK(c->d_out.ensure(outTotal + 16));
     CK(c->d_scratch.ensure(scratchTotal + 16));
+    CK(c->d_meta.ensure(metaTotal + 16));
     if (outTotal + 16 > c->h_out_cap) { if (c->h_out) cudaFreeHost(c->h_out); c->h_out = nullptr; c->h_out_cap = 0; size_t want = outTotal + outTotal / 2 + 64; CK(cudaMallocHost((void**)&c->h_out, want)); c->h_out_cap = want; }
     CK(cudaMemcpyAsync(c->d_in.p, c->h_in, inBytes, cudaMemcpyHostToDevice, c->stream));
     c->ctr.h2d_bytes += (int64_t)inBytes;
@@ -777,13 +994,17 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
     prm.m = c->dm;
     prm.gaps = c->d_gaps.p; prm.read_len = c->d_rlen.p; prm.read_off = c->d_roff.p; prm.read_mate = c->d_rmate.p;
     prm.read_flags = c->d_rfl.p; prm.read_jlo = c->d_jlo.p; prm.read_jcut = c->d_jcut.p; prm.codes = c->d_codes.p;
-    prm.flank = c->d_flank.p; prm.pile_l = c->d_pl.p; prm.pile_r = c->d_pr.p;
+    prm.flank = c->d_flank.p; prm.pile_l = c->d_pl.p; prm.pile_r = c->d_pr.p; prm.read_gap = c->d_rgap.p; prm.lfrf = c->d_lfrf.p; prm.meta = c->d_meta.p;
     prm.items = (const DevItem*)c->d_in.p; prm.in_arena = c->d_in.p + itemsBytes; prm.out_arena = c->d_out.p; prm.scratch = c->d_scratch.p;
     prm.counters = c->d_ctr.p;
 
+    int launches = 0;
+    if (c->flankDirty) {      // flank products of every read of the batch, once (model and batch are both resident now)
+        if (c->nReads > 0) { fb_flank_kernel<<<c->nReads, 128, 0, c->stream>>>(prm, c->nReads); CK(cudaGetLastError()); launches++; }
+        c->flankDirty = false;
+    }
     // one launch per shared-memory bucket, on its own stream, so small items run at high occupancy beside large ones
     CK(cudaEventRecord(c->ev0, c->stream));
-    int launches = 0;
     const int* d_order = (const int*)(c->d_in.p + orderOff);
     for (int b = 0; b <= kNumBuckets; b++) {
         if (!bucketCount[b]) continue;
@@ -797,12 +1018,13 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
     }
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaMemcpyAsync(c->h_out, c->d_out.p, outTotal, cudaMemcpyDeviceToHost, c->stream));
-    unsigned long long hc[4] = {0, 0, 0, 0};
+    unsigned long long hc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     CK(cudaMemcpyAsync(hc, c->d_ctr.p, sizeof hc, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->ctr.device_ms += ms; c->ctr.kernel_launches += launches; c->ctr.d2h_bytes += (int64_t)outTotal;
     c->ctr.placements_p1 = (int64_t)hc[0]; c->ctr.placements_p2 = (int64_t)hc[1]; c->ctr.base_terms = (int64_t)hc[2];
+    c->ctr.lane_steps_p1 = (int64_t)hc[3]; c->ctr.lane_steps_p2 = (int64_t)hc[4];
     for (int i = 0; i < n; i++) {
         FbItemOut* H = (FbItemOut*)(c->h_out + di[i].out_off);
         const DevGap& g = c->hGaps[items[i].gap];

@@ -158,6 +158,9 @@ typedef struct {
     int64_t kernel_launches;
     double device_ms;           /* CUDA-event time of the kernels launched by fb_em_run */
     int64_t h2d_bytes, d2h_bytes;
+    int64_t lane_steps_p1;      /* pass-1 gap-row terms actually executed (warp steps x 32 lanes): flank terms come from the
+                                   per-gap cache and inadmissible offsets are never visited, so this is below base_terms */
+    int64_t lane_steps_p2;      /* pass-2 terms actually executed (pruned against the pass-1 winner) */
 } FbCounters;
 
 fb_status fb_ctx_create(int32_t device, fb_ctx** out);
