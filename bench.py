@@ -246,6 +246,8 @@ def main():
                     "note": "through fb_fillgaps_main: files -> model -> per-gap control on host threads -> engine; reference-equivalent pass-1 placements / wall",
                     "gaps_per_s": (len(open(os.path.join(case, "partial", "Temp", "gapInfo.txt")).readlines()) * world * a.steps) / dt_max,
                     "host_seconds_per_step": {k: sum(m[k] for m in metrics) / a.steps for k in ("t_load", "t_model", "t_prepare", "t_fill", "t_write")}},
+            "executed": {"pass1_gap_row_lane_steps": sum(m.get("lane_steps_p1", 0) for m in metrics), "pass2_lane_steps": sum(m.get("lane_steps_p2", 0) for m in metrics),
+                         "algorithmic_base_terms": terms, "note": "rank 0, all timed steps: terms the kernel walked (flank terms cached per gap, pass 2 pruned) vs. terms the reference evaluates"},
             "gpu_launches": int(launches_all), "device_placements_p1": dev_p1_all, "device_placements_p2": dev_p2_all, "roofline": roof}
     if world == 1 and not a.no_cpu_baseline and fc.have_reference():
         sample = prepare_case(os.path.join(base, "sample"), SAMPLE, 1102)

@@ -44,6 +44,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/figbird_b200.h"
@@ -53,9 +54,9 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxSmem = 200 * 1024;      // dynamic shared memory we opt in to (227 KB is the sm_100 limit)
-constexpr int kChunkWant = 32 * 1024;     // weights + read-code staging we ask for per CTA when the reads allow it
+constexpr int kChunkWant = 72 * 1024;     // weights + read-code staging we ask for per CTA when the reads allow it
 constexpr int kNumBuckets = 4;
-__host__ __device__ constexpr int bucketCap(int b) { return b == 0 ? 36 * 1024 : b == 1 ? 72 * 1024 : b == 2 ? 108 * 1024 : kMaxSmem; }
+__host__ __device__ constexpr int bucketCap(int b) { return b == 0 ? 36 * 1024 : b == 1 ? 72 * 1024 : b == 2 ? 112 * 1024 : kMaxSmem; }
 
 struct DevGap { long long gap_start; int mode, orig_len, n_reads, read_begin, flank_len, flank_begin, pile_len, pile_begin; };
 
@@ -94,20 +95,18 @@ struct Params {
 //   table region (shared memory, or a global scratch slice for very long candidates):
 //     UT[5][S] double2 {P, E-P}: plane c = read base code, entry r = gap row r mod Lg for r < S = Lg + maxLenPad
 //     (cyclic extension, so that a lane's address is linear in the read base index),
-//     C[5][Lg] countsGap, GP[split][5][Lg] gather partials, NC[5][Lg] new_counts_gap, G[rows] gapString codes,
+//     C[5][Lg] countsGap, NC[5][Lg] new_counts_gap, G[rows] gapString codes,
 //     PREV[Lg] previous hard consensus
 //   local region (always shared): ME[k] = e, MT2[k] = {1-e-ins-del, e}, ETP[25], then per chunk of reads RC (codes) and W.
-struct Plan { int S, rows, split, oUT, oC, oGP, oNC, oG, oPREV, tableBytes, oME, oMT2, oETP, localFixed, maxLenPad, nMax, perRead; };
+struct Plan { int S, rows, oUT, oC, oNC, oG, oPREV, tableBytes, oME, oMT2, oETP, localFixed, maxLenPad, nMax, perRead; };
 __host__ __device__ inline int al16(int x) { return (x + 15) & ~15; }
 __host__ __device__ inline Plan makePlan(int Lg, int F, int modelLen, int maxLen, int mode, int bandMax) {
     Plan p;
     p.maxLenPad = (maxLen + 15) & ~15;
     p.S = Lg + p.maxLenPad; p.rows = Lg + 2 * F;
-    p.split = (Lg >= 128 || Lg <= 0) ? 1 : (kThreads / Lg > 8 ? 8 : kThreads / Lg);
     int o = 0;
     p.oUT = o; o += 16 * 5 * p.S;
     p.oC = o; o += 8 * 5 * Lg;
-    p.oGP = o; o += (p.split > 1) ? 8 * 5 * Lg * p.split : 0;
     p.oNC = o; o += 4 * 5 * Lg;
     p.oG = o; o += al16(p.rows);
     p.oPREV = o; o += al16(Lg);
@@ -120,7 +119,7 @@ __host__ __device__ inline Plan makePlan(int Lg, int F, int modelLen, int maxLen
     int n = (mode == FB_MODE_UNMAPPED) ? (maxLen + Lg - 1) : (maxLen - 1);
     if (mode == FB_MODE_UNMAPPED && bandMax < n) n = bandMax;     // unmapped reads always pass through the insert-size filter
     p.nMax = n > 1 ? n : 1;
-    p.perRead = 8 * p.nMax + p.maxLenPad;
+    p.perRead = 8 * p.nMax + p.maxLenPad + 40;       // weights + codes + record + threshold
     return p;
 }
 
@@ -258,7 +257,6 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
     unsigned char* const lbase = TSMEM ? smem + pl.tableBytes : smem;
     double2* const UT = (double2*)(tbase + pl.oUT);
     double* const C = (double*)(tbase + pl.oC);
-    double* const GP = (double*)(tbase + pl.oGP);
     int* const NC = (int*)(tbase + pl.oNC);
     unsigned char* const G = tbase + pl.oG;
     unsigned char* const PREV = tbase + pl.oPREV;
@@ -324,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
         sumTerms = (long long)s_terms;
     }
     const int totalW = (int)sumN;
-    const bool singleChunk = (8LL * totalW + (long long)R * mlp) <= (long long)chunkBytes;
+    const bool singleChunk = (8LL * totalW + (long long)R * (mlp + 40) + 64) <= (long long)chunkBytes;
     int prevValid = 0;   // previous hard consensus present (uniform)
 
     auto storeRow = [&](int x, const double p[4], const double e[5]) {     // gap row x and its cyclic copies
@@ -366,33 +364,59 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
         for (int q = tid; q < R; q += kThreads) { oP1[q] = -1.0; mt.x1[q] = INT_MIN; }
     }
 
-    unsigned char* const RC = chunkBase;                                    // [reads in chunk][mlp]
-    auto stageReads = [&](int q0, int q1) {   // read codes of the chunk -> RC
-        const int n = (q1 - q0) * mlp;
+    // ---- chunk region: per-read records RM[nq+1], pass-2 thresholds THR[nq], read codes RC[nq][mlp], weights W
+    struct RMeta { int xlo, wrel, n, packed, rel, u1, u2, x1; };     // packed = len | jlo<<8 | jhi<<16 | flags<<24; wrel/u1/u2 relative to the chunk
+    RMeta* const RM = (RMeta*)chunkBase;
+    int nqCur = 0;                       // reads in the resident chunk (uniform)
+    double* THR = nullptr; unsigned char* RC = nullptr; double* W = nullptr;
+    auto carveChunk = [&](int nq) {
+        nqCur = nq;
+        THR = (double*)(chunkBase + 32 * (size_t)(nq + 1));
+        RC = (unsigned char*)THR + al16(8 * nq);
+        W = (double*)(RC + (size_t)nq * mlp);
+    };
+    auto stageReads = [&](int q0, int q1) {   // read records and codes of the chunk
+        const int nq = q1 - q0;
+        carveChunk(nq);
+        const int wb = mt.woff[q0], u1b = mt.u1[q0], u2b = mt.u2[q0];
+        for (int ql = tid; ql <= nq; ql += kThreads) {
+            const int q = q0 + ql;
+            RMeta r;
+            r.wrel = mt.woff[q] - wb; r.u1 = mt.u1[q] - u1b; r.u2 = mt.u2[q] - u2b;
+            if (ql < nq) {
+                const int qi = g.read_begin + q; const int len = prm.read_len[qi];
+                r.xlo = mt.xlo[q]; r.n = mt.woff[q + 1] - mt.woff[q]; r.rel = prm.read_mate[qi]; r.x1 = mt.x1[q];
+                r.packed = len | (prm.read_jlo[qi] << 8) | ((len - prm.read_jcut[qi]) << 16) | (prm.read_flags[qi] << 24);
+            } else { r.xlo = 0; r.n = 0; r.rel = 0; r.x1 = INT_MIN; r.packed = 0; }
+            RM[ql] = r;
+        }
+        const int n = nq * mlp;
         for (int i = tid; i < n; i += kThreads) {
             const int ql = i / mlp, j = i - ql * mlp;
             const int qi = g.read_begin + q0 + ql;
             RC[i] = (j < prm.read_len[qi]) ? prm.codes[prm.read_off[qi] + j] : (unsigned char)4;
         }
     };
-    // reads [q0, q1) whose codes + weight rows fit the chunk region (at least one read)
+    // reads [q0, q1) whose records + codes + weight rows fit the chunk region (at least one read)
     auto chunkEnd = [&](int q0) -> int {
         if (singleChunk) return R;
         __syncthreads();
         if (tid == 0) {
-            int q = q0; long long bytes = 0;
-            while (q < R) { const long long nb = 8LL * (mt.woff[q + 1] - mt.woff[q]) + mlp; if (q > q0 && bytes + nb > chunkBytes) break; bytes += nb; q++; }
+            int q = q0; long long bytes = 64;
+            while (q < R) { const long long nb = 8LL * (mt.woff[q + 1] - mt.woff[q]) + mlp + 40; if (q > q0 && bytes + nb > chunkBytes) break; bytes += nb; q++; }
             s_q1 = q;
         }
         __syncthreads();
         return s_q1;
     };
-    // read that owns work unit `target` in a prefix array (largest q in [q0, q1) with pre[q] <= target)
-    auto findRead = [&](const int* pre, int q0, int q1, int target) -> int {
-        int lo = q0, hi = q1 - 1;
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (pre[mid] <= target) lo = mid; else hi = mid - 1; }
+    // read of the resident chunk that owns work unit `target` (largest ql with prefix[ql] <= target); U2 selects the pass-2 prefix
+    auto findRead = [&](bool U2, int target) -> int {
+        int lo = 0, hi = nqCur - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; const int v = U2 ? RM[mid].u2 : RM[mid].u1; if (v <= target) lo = mid; else hi = mid - 1; }
         return lo;
     };
+    if (it.kind == FB_ITEM_EM) for (int q = tid; q < R; q += kThreads) mt.x1[q] = INT_MIN;
+    __syncthreads();
     if (singleChunk) stageReads(0, R);
     __syncthreads();
 
@@ -420,19 +444,16 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
         for (int q0 = 0, q1; q0 < R; q0 = q1) {
             q1 = chunkEnd(q0);
             if (!singleChunk) { stageReads(q0, q1); __syncthreads(); }
-            double* const W = (double*)(chunkBase + (size_t)(q1 - q0) * mlp);
-            const int wbase = mt.woff[q0], ubase = mt.u2[q0];
+            const int nq = q1 - q0;
             // exact product at the offset that won pass 1: every other offset only has to beat it
-            for (int ql = tid; ql < q1 - q0; ql += kThreads) {
-                const int q = q0 + ql, qi = g.read_begin + q;
-                const int x1 = mt.x1[q];
+            for (int ql = tid; ql < nq; ql += kThreads) {
+                const RMeta r = RM[ql];
                 double thr = 0.0;
-                if (x1 != INT_MIN && m.prunable) {
-                    const int len = prm.read_len[qi], fl = prm.read_flags[qi];
-                    const int jlo = prm.read_jlo[qi], jhi = len - prm.read_jcut[qi];
-                    const bool rev = fl & FB_READ_REVERSE;
+                if (r.x1 != INT_MIN && m.prunable) {
+                    const int len = r.packed & 0xff, jlo = (r.packed >> 8) & 0xff, jhi = (r.packed >> 16) & 0xff;
+                    const bool rev = (r.packed >> 24) & FB_READ_REVERSE;
                     const unsigned char* rc = RC + ql * mlp;
-                    const unsigned char* gs = G + F + x1;
+                    const unsigned char* gs = G + F + r.x1;
                     double p = 1.0;
                     for (int j = jlo; j < jhi; j++) {
                         const int c = rc[j], f = gs[j];
@@ -441,26 +462,26 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
                     }
                     thr = p;
                 }
-                mt.thr[q] = thr;
+                THR[ql] = thr;
             }
             __syncthreads();
-            const int units = mt.u2[q1] - ubase;
+            const int units = RM[nq].u2;
             for (int u = warp; u < units; u += kWarps) {
-                const int q = findRead(mt.u2, q0, q1, u + ubase), ql = q - q0, qi = g.read_begin + q;
-                const int ch = u + ubase - mt.u2[q];
-                const int len = prm.read_len[qi], fl = prm.read_flags[qi];
-                const int jlo = prm.read_jlo[qi], jhi = len - prm.read_jcut[qi];
-                const int xlo = mt.xlo[q], n = mt.woff[q + 1] - mt.woff[q];
-                const double thr = mt.thr[q];
-                const int x1 = (thr > 0.0) ? mt.x1[q] : INT_MIN;      // known exactly: not walked again
+                const int ql = findRead(true, u);
+                const RMeta r = RM[ql];
+                const int ch = u - r.u2;
+                const int len = r.packed & 0xff, jlo = (r.packed >> 8) & 0xff, jhi = (r.packed >> 16) & 0xff;
+                const int xlo = r.xlo, n = r.n;
+                const double thr = THR[ql];
+                const int x1 = (thr > 0.0) ? r.x1 : INT_MIN;      // known exactly: not walked again
                 const int ia = ch * 64 + lane, ib = ia + 32;
                 const int xa = xlo + ia, xb = xlo + ib;
                 const bool ina = ia < n, inb = ib < n;
-                bool acta = ina && xa != x1, actb = inb && xb != x1;
+                const bool acta = ina && xa != x1, actb = inb && xb != x1;
                 double pa = 1.0, pb = 1.0;
                 if (__any_sync(0xffffffffu, acta || actb)) {
                     const int ra = F + (ina ? xa : xlo), rb = F + (inb ? xb : (ina ? xa : xlo));
-                    const bool rev = fl & FB_READ_REVERSE;
+                    const bool rev = (r.packed >> 24) & FB_READ_REVERSE;
                     const unsigned char* rc = RC + ql * mlp;
                     const unsigned char* ga = G + ra; const unsigned char* gb = G + rb;
                     int j = jlo, steps = 0;
@@ -480,16 +501,16 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
                     }
                     if (lane == 0) atomicAdd(&s_lane2, (unsigned long long)steps * 64ull);
                 }
-                if (ina) W[mt.woff[q] - wbase + ia] = acta ? pa : thr;
-                if (inb) W[mt.woff[q] - wbase + ib] = actb ? pb : thr;
+                if (ina) W[r.wrel + ia] = acta ? pa : thr;
+                if (inb) W[r.wrel + ib] = actb ? pb : thr;
             }
             __syncthreads();
             // first maximum over ascending offsets (strict >), accept test, unit votes (Figbird.cpp:3787-3912)
-            for (int ql = warp; ql < q1 - q0; ql += kWarps) {
-                const int q = q0 + ql, qi = g.read_begin + q;
-                const int len = prm.read_len[qi];
-                const int xlo = mt.xlo[q], n = mt.woff[q + 1] - mt.woff[q];
-                const double* Wq = W + (mt.woff[q] - wbase);
+            for (int ql = warp; ql < nq; ql += kWarps) {
+                const RMeta r = RM[ql];
+                const int q = q0 + ql, len = r.packed & 0xff;
+                const int xlo = r.xlo, n = r.n;
+                const double* Wq = W + r.wrel;
                 double best = -1.0; int bestI = 0x7fffffff;
                 for (int i = lane; i < n; i += 32) { double v = Wq[i]; if (v > best) { best = v; bestI = i; } }
 #pragma unroll
@@ -522,8 +543,13 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
     } else {
         const int maxCalls = it.max_rounds + ((it.flags & FB_FLAG_EXTRA_PASS) ? 1 : 0);
         bool emDone = it.max_rounds <= 0;
-        const int split = pl.split;
         const long long offLg = (long long)Lg - g.orig_len;
+        // gather geometry: a task = 4 consecutive gap rows x one part of the reads; parts are combined in order through
+        // a scratch that aliases the row tables (dead between the walk and the M-step), so only when all reads are resident
+        const int nG = (Lg + 3) >> 2, tpp = (nG + 31) & ~31;
+        int split = 1;
+        if (singleChunk && Lg > 0) { split = kThreads / tpp; const int cap = (2 * S) / Lg; split = max(1, min(min(split, cap), 8)); }
+        double* const GP = (double*)UT;
         for (int call = 0; call < maxCalls; call++) {
             const bool extra = emDone;
             const int slot = (it.flags & FB_FLAG_RECORD_ALL) ? call : 0;
@@ -533,17 +559,16 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
             for (int q0 = 0, q1; q0 < R; q0 = q1) {
                 q1 = chunkEnd(q0);
                 if (!singleChunk) { stageReads(q0, q1); __syncthreads(); }
-                double* const W = (double*)(chunkBase + (size_t)(q1 - q0) * mlp);
-                const int wbase = mt.woff[q0], ubase = mt.u1[q0];
+                const int nq = q1 - q0;
                 // ---- gap-row products of every admissible placement: cyclic diagonal walk
-                const int units = (Lg > 0) ? mt.u1[q1] - ubase : 0;
+                const int units = (Lg > 0) ? RM[nq].u1 : 0;
                 for (int u = warp; u < units; u += kWarps) {
-                    const int q = findRead(mt.u1, q0, q1, u + ubase), ql = q - q0, qi = g.read_begin + q;
-                    const int uu = u + ubase - mt.u1[q];
-                    const int len = prm.read_len[qi], fl = prm.read_flags[qi];
-                    const int jlo = prm.read_jlo[qi], jhi = len - prm.read_jcut[qi];
-                    const int xlo = mt.xlo[q], n = mt.woff[q + 1] - mt.woff[q];
-                    double* const Wq = W + (mt.woff[q] - wbase);
+                    const int ql = findRead(false, u);
+                    const RMeta r = RM[ql];
+                    const int uu = u - r.u1;
+                    const int len = r.packed & 0xff, jlo = (r.packed >> 8) & 0xff, jhi = (r.packed >> 16) & 0xff;
+                    const int xlo = r.xlo, n = r.n;
+                    double* const Wq = W + r.wrel;
                     const bool full = n >= Lg;
                     const int nl = full ? Lg : n;
                     const int idx = uu * 32 + lane;
@@ -556,41 +581,58 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
                     int xm = xi % Lg; if (xm < 0) xm += Lg;
                     const int m0 = (xm + js) / Lg;
                     int x0cur = xm - m0 * Lg;          // placement whose segment contains read base js
-                    int jw = (m0 + 1) * Lg - xm;       // read base at which the walk re-enters gap row 0
+                    int jw = (m0 + 1) * Lg - xm;       // read base at which the walk re-enters gap row 0 (> js)
                     const double2* ptr = UT + xm;      // + j: cyclically extended table, plane 0
                     const unsigned char* rc = RC + ql * mlp;
                     const double* me = ME; int kstep = 1, kb = 0;
-                    if (fl & FB_READ_REVERSE) { kb = len - 1; kstep = -1; }
+                    if ((r.packed >> 24) & FB_READ_REVERSE) { kb = len - 1; kstep = -1; }
                     double acc = 1.0;
-                    auto stepv = [&](int j, const double2 v, double e) {
+                    auto mul = [&](const double2 v, double e) { acc = __dmul_rn(acc, __fma_rn(e, v.y, v.x)); };
+                    auto wrap = [&](int j) {
                         if (j == jw) {      // the walk re-enters gap row 0: the running product belongs to placement x0cur
                             if (active && (unsigned)(x0cur - xlo) < (unsigned)n) Wq[x0cur - xlo] = acc;
                             acc = 1.0; x0cur -= Lg; jw += Lg;
                         }
-                        acc = __dmul_rn(acc, __fma_rn(e, v.y, v.x));
                     };
+                    // read bases [j, stop): CHECK = some lane of the warp may wrap in this stretch
+                    auto run = [&](auto CHECK, int& j, int stop) {
+                        for (; j < stop && (j & 3); j++) { if (CHECK.value) wrap(j); mul(ptr[rc[j] * S + j], me[kb + kstep * j]); }
+                        for (; j + 4 <= stop; j += 4) {
+                            const unsigned cw = *(const unsigned*)(rc + j);
+                            const double2* pj = ptr + j;
+                            const double2 v0 = pj[(cw & 0xff) * S], v1 = pj[((cw >> 8) & 0xff) * S + 1], v2 = pj[((cw >> 16) & 0xff) * S + 2], v3 = pj[(cw >> 24) * S + 3];
+                            const double e0 = me[kb + kstep * j], e1 = me[kb + kstep * (j + 1)], e2 = me[kb + kstep * (j + 2)], e3 = me[kb + kstep * (j + 3)];
+                            if (CHECK.value) wrap(j);
+                            mul(v0, e0);
+                            if (CHECK.value) wrap(j + 1);
+                            mul(v1, e1);
+                            if (CHECK.value) wrap(j + 2);
+                            mul(v2, e2);
+                            if (CHECK.value) wrap(j + 3);
+                            mul(v3, e3);
+                        }
+                        for (; j < stop; j++) { if (CHECK.value) wrap(j); mul(ptr[rc[j] * S + j], me[kb + kstep * j]); }
+                    };
+                    // lanes hold consecutive diagonals, so their wrap points fill a window of at most 32 consecutive read bases per period
+                    int wmin = __reduce_min_sync(0xffffffffu, jw), wmax = __reduce_max_sync(0xffffffffu, jw);
                     int j = js;
-                    for (; j < je && (j & 3); j++) stepv(j, ptr[rc[j] * S + j], me[kb + kstep * j]);
-                    for (; j + 4 <= je; j += 4) {
-                        const unsigned cw = *(const unsigned*)(rc + j);
-                        const double2* pj = ptr + j;
-                        const double2 v0 = pj[(cw & 0xff) * S], v1 = pj[((cw >> 8) & 0xff) * S + 1], v2 = pj[((cw >> 16) & 0xff) * S + 2], v3 = pj[(cw >> 24) * S + 3];
-                        const double e0 = me[kb + kstep * j], e1 = me[kb + kstep * (j + 1)], e2 = me[kb + kstep * (j + 2)], e3 = me[kb + kstep * (j + 3)];
-                        stepv(j, v0, e0); stepv(j + 1, v1, e1); stepv(j + 2, v2, e2); stepv(j + 3, v3, e3);
+                    while (j < je) {
+                        run(std::false_type(), j, min(je, wmin));
+                        run(std::true_type(), j, min(je, wmax + 1));
+                        wmin += Lg; wmax += Lg;
                     }
-                    for (; j < je; j++) stepv(j, ptr[rc[j] * S + j], me[kb + kstep * j]);
                     if (active && (unsigned)(x0cur - xlo) < (unsigned)n) Wq[x0cur - xlo] = acc;
                     if (lane == 0) atomicAdd(&s_lane1, (unsigned long long)(je - js) * 32ull);
                 }
                 __syncthreads();
                 // ---- finish every placement: insert pdf x left-flank product x gap product x right-flank product,
                 //      per-read maximum (value and offset), soft weight in place
-                for (int ql = warp; ql < q1 - q0; ql += kWarps) {
+                for (int ql = warp; ql < nq; ql += kWarps) {
+                    const RMeta r = RM[ql];
                     const int q = q0 + ql, qi = g.read_begin + q;
-                    const int len = prm.read_len[qi], fl = prm.read_flags[qi], rel = prm.read_mate[qi];
-                    const int jlo = prm.read_jlo[qi], jhi = len - prm.read_jcut[qi];
-                    const int xlo = mt.xlo[q], n = mt.woff[q + 1] - mt.woff[q];
-                    double* const Wq = W + (mt.woff[q] - wbase);
+                    const int len = r.packed & 0xff, jlo = (r.packed >> 8) & 0xff, jhi = (r.packed >> 16) & 0xff, fl = (r.packed >> 24) & 0xff;
+                    const int xlo = r.xlo, n = r.n, rel = r.rel;
+                    double* const Wq = W + r.wrel;
                     const double* LF = prm.lfrf + 2 * prm.read_off[qi];
                     const double* RF = LF + len;
                     double best = 0.0; int bestI = 0x7fffffff;
@@ -615,43 +657,70 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
                         double ov = __shfl_xor_sync(0xffffffffu, best, o); int oi = __shfl_xor_sync(0xffffffffu, bestI, o);
                         if (ov > best || (ov == best && oi < bestI)) { best = ov; bestI = oi; }
                     }
-                    if (lane == 0) { oP1[(size_t)slot * R + q] = (best > 0.0) ? best : -1.0; mt.x1[q] = (best > 0.0) ? xlo + bestI : INT_MIN; }
+                    if (lane == 0) {
+                        const int x1 = (best > 0.0) ? xlo + bestI : INT_MIN;
+                        oP1[(size_t)slot * R + q] = (best > 0.0) ? best : -1.0; RM[ql].x1 = x1; mt.x1[q] = x1;
+                    }
                 }
                 __syncthreads();
-                // ---- gather the weights of this chunk into the gap rows in a fixed order (deterministic, no FP atomics):
-                // thread (row x, part s) sums reads s, s+split, ... ascending, read base ascending; parts are added in order.
-                for (int idx = tid; idx < Lg * split; idx += kThreads) {
-                    const int s = idx / Lg, x = idx - s * Lg;
-                    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
-                    for (int ql = s; ql < q1 - q0; ql += split) {
-                        const int q = q0 + ql, qi = g.read_begin + q;
-                        const int n = mt.woff[q + 1] - mt.woff[q];
-                        if (n <= 0) continue;
-                        const int len = prm.read_len[qi];
-                        const int xlo = mt.xlo[q], xhi = xlo + n - 1;
+                // ---- gather the weights of this chunk into the gap rows in a fixed order (deterministic, no FP atomics).
+                // A thread owns 4 consecutive rows x..x+3 and one part of the reads; all lanes of a warp walk the same read
+                // base j (uniform code -> uniform branch), row x+b takes the weight of placement x+b-j: one new weight
+                // per step slides through four registers.
+                for (int idx = tid; idx < tpp * split; idx += kThreads) {
+                    const int s = idx / tpp, gi = idx - s * tpp;
+                    const int x = gi << 2;
+                    const int xw0 = (gi - lane) << 2, xw1 = min(Lg - 1, xw0 + 127);      // rows of this warp
+                    double a[4][5];
+#pragma unroll
+                    for (int b = 0; b < 4; b++)
+#pragma unroll
+                        for (int k = 0; k < 5; k++) a[b][k] = 0.0;
+                    if (xw0 < Lg) for (int ql = s; ql < nq; ql += split) {
+                        const RMeta r = RM[ql];
+                        if (r.n <= 0) continue;
+                        const int len = r.packed & 0xff;
+                        const int xlo = r.xlo, n = r.n;
+                        // placement x0 = row - j in [xlo, xlo + n)  <=>  j in [row - xlo - n + 1, row - xlo]
+                        const int ja = max(0, xw0 - xlo - n + 1), jb = min(len - 1, xw1 - xlo);
+                        if (ja > jb) continue;
                         const unsigned char* rc = RC + ql * mlp;
-                        // x0 = x - j in [xlo, xhi]  <=>  j in [x - xhi, x - xlo]
-                        const int ja = max(0, x - xhi), jb = min(len - 1, x - xlo);
-                        const double* wr = W + (mt.woff[q] - wbase) - xlo;
+                        const double* wr = W + r.wrel;
+                        auto ld = [&](int i) -> double { return ((unsigned)i < (unsigned)n) ? wr[i] : 0.0; };
+                        int i0 = x - ja - xlo;                 // weight index of row x at read base ja; row x+b: i0 + b
+                        double w0 = ld(i0), w1 = ld(i0 + 1), w2 = ld(i0 + 2), w3 = ld(i0 + 3);
                         for (int j = ja; j <= jb; j++) {
-                            const double w = wr[x - j];
-                            switch (rc[j]) { case 0: a0 = __dadd_rn(a0, w); break; case 1: a1 = __dadd_rn(a1, w); break; case 2: a2 = __dadd_rn(a2, w); break; case 3: a3 = __dadd_rn(a3, w); break; default: a4 = __dadd_rn(a4, w); }
+                            switch (rc[j]) {
+                                case 0: a[0][0] = __dadd_rn(a[0][0], w0); a[1][0] = __dadd_rn(a[1][0], w1); a[2][0] = __dadd_rn(a[2][0], w2); a[3][0] = __dadd_rn(a[3][0], w3); break;
+                                case 1: a[0][1] = __dadd_rn(a[0][1], w0); a[1][1] = __dadd_rn(a[1][1], w1); a[2][1] = __dadd_rn(a[2][1], w2); a[3][1] = __dadd_rn(a[3][1], w3); break;
+                                case 2: a[0][2] = __dadd_rn(a[0][2], w0); a[1][2] = __dadd_rn(a[1][2], w1); a[2][2] = __dadd_rn(a[2][2], w2); a[3][2] = __dadd_rn(a[3][2], w3); break;
+                                case 3: a[0][3] = __dadd_rn(a[0][3], w0); a[1][3] = __dadd_rn(a[1][3], w1); a[2][3] = __dadd_rn(a[2][3], w2); a[3][3] = __dadd_rn(a[3][3], w3); break;
+                                default: a[0][4] = __dadd_rn(a[0][4], w0); a[1][4] = __dadd_rn(a[1][4], w1); a[2][4] = __dadd_rn(a[2][4], w2); a[3][4] = __dadd_rn(a[3][4], w3);
+                            }
+                            i0--;
+                            w3 = w2; w2 = w1; w1 = w0; w0 = ld(i0);
                         }
                     }
-                    if (split == 1) {
-                        C[x] = __dadd_rn(C[x], a0); C[Lg + x] = __dadd_rn(C[Lg + x], a1); C[2 * Lg + x] = __dadd_rn(C[2 * Lg + x], a2);
-                        C[3 * Lg + x] = __dadd_rn(C[3 * Lg + x], a3); C[4 * Lg + x] = __dadd_rn(C[4 * Lg + x], a4);
-                    } else {
-                        double* gp = GP + (size_t)s * 5 * Lg + x;
-                        gp[0] = a0; gp[Lg] = a1; gp[2 * Lg] = a2; gp[3 * Lg] = a3; gp[4 * Lg] = a4;
+                    if (gi < nG) {
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            const int row = x + b;
+                            if (row < Lg) {
+#pragma unroll
+                                for (int k = 0; k < 5; k++) {
+                                    if (split == 1) C[k * Lg + row] = __dadd_rn(C[k * Lg + row], a[b][k]);
+                                    else GP[((size_t)s * 5 + k) * Lg + row] = a[b][k];
+                                }
+                            }
+                        }
                     }
                 }
                 if (split > 1) {
                     __syncthreads();
                     for (int i = tid; i < 5 * Lg; i += kThreads) {
-                        double a = C[i];
-                        for (int s = 0; s < split; s++) a = __dadd_rn(a, GP[(size_t)s * 5 * Lg + i]);
-                        C[i] = a;
+                        double acc = C[i];
+                        for (int s = 0; s < split; s++) acc = __dadd_rn(acc, GP[(size_t)s * 5 * Lg + i]);
+                        C[i] = acc;
                     }
                 }
                 __syncthreads();
@@ -938,14 +1007,14 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
         d.meta_off = (long long)metaTotal; metaTotal += metaBytes(R);
         const Plan pl = makePlan(Lg, g.flank_len, c->dm.max_read_len, ml, g.mode, bandMax);
         const long long want = std::min<long long>((long long)pl.perRead * std::max(R, 1), kChunkWant);
-        const long long chunk = std::max<long long>(want, pl.perRead) + 32;
-        if ((long long)pl.tableBytes + pl.localFixed + pl.perRead + 32 <= kMaxSmem) {
+        const long long chunk = std::max<long long>(want, pl.perRead) + 128;
+        if ((long long)pl.tableBytes + pl.localFixed + pl.perRead + 128 <= kMaxSmem) {
             d.tables_in_smem = 1; d.scratch_off = -1;
             const int need = (int)std::min<long long>(kMaxSmem, (long long)pl.tableBytes + pl.localFixed + chunk);
             int b = 0; while (b < kNumBuckets - 1 && need > bucketCap(b)) b++;
             bucketOf[i] = b; bucketSmem[b] = std::max(bucketSmem[b], need);
         } else {
-            if ((long long)pl.localFixed + pl.perRead + 32 > kMaxSmem) { c->err = "candidate length too large for one weight row in shared memory"; return FB_ERR_ARG; }
+            if ((long long)pl.localFixed + pl.perRead + 128 > kMaxSmem) { c->err = "candidate length too large for one weight row in shared memory"; return FB_ERR_ARG; }
             d.tables_in_smem = 0; d.scratch_off = (long long)scratchTotal; scratchTotal += (size_t)pl.tableBytes;
             bucketOf[i] = kNumBuckets; bucketSmem[kNumBuckets] = std::max(bucketSmem[kNumBuckets], (int)std::min<long long>(kMaxSmem, (long long)pl.localFixed + chunk));
         }
