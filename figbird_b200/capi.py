@@ -52,7 +52,7 @@ class FbItemOut(C.Structure):
 class FbCounters(C.Structure):
     _fields_ = [("placements_p1", C.c_int64), ("placements_p2", C.c_int64), ("base_terms", C.c_int64), ("kernel_launches", C.c_int64),
                 ("device_ms", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("lane_steps_p1", C.c_int64), ("lane_steps_p2", C.c_int64)]
+                ("lane_steps_p1", C.c_int64), ("lane_steps_p2", C.c_int64), ("device_union_ms", C.c_double)]
 
 
 EXPORTS = ["fb_ctx_create", "fb_ctx_destroy", "fb_last_error", "fb_engine_name", "fb_model_upload", "fb_batch_upload", "fb_em_run",

@@ -43,6 +43,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -829,6 +830,11 @@ struct fb_ctx {
     FbCounters ctr{};
 };
 
+// Kernel intervals of all contexts on one physical device, on one time base (an epoch event per device): contexts that
+// share a GPU overlap their kernels, so the device time of a run is the union of the intervals, not the sum.
+struct DevClock { std::mutex mu; cudaEvent_t epoch = nullptr; double lastEnd = 0, unionMs = 0; };
+static DevClock g_clock[64];
+
 extern "C" const char* fb_engine_name(void) { return "cuda-sm100a"; }
 extern "C" const char* fb_last_error(const fb_ctx* c) { return c ? c->err.c_str() : "null context"; }
 
@@ -850,6 +856,10 @@ extern "C" fb_status fb_ctx_create(int32_t device, fb_ctx** out) {
     CK(cudaFuncSetAttribute(fb_em_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     for (int b = 0; b <= kNumBuckets; b++) { CK(cudaStreamCreateWithFlags(&c->bstream[b], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->bev[b], cudaEventDisableTiming)); }
     CK(c->d_ctr.ensure(8)); CK(cudaMemset(c->d_ctr.p, 0, 8 * sizeof(unsigned long long)));
+    if (device < 64) {
+        DevClock& k = g_clock[device]; std::lock_guard<std::mutex> l(k.mu);
+        if (!k.epoch) { CK(cudaEventCreate(&k.epoch)); CK(cudaEventRecord(k.epoch, c->stream)); CK(cudaEventSynchronize(k.epoch)); }
+    }
     return FB_OK;
 }
 
@@ -960,6 +970,7 @@ extern "C" fb_status fb_batch_upload(fb_ctx* c, const FbGapBatch* b) {
 extern "C" fb_status fb_get_counters(const fb_ctx* c, FbCounters* out) {
     if (!c || !out) return FB_ERR_ARG;
     *out = c->ctr;
+    if (c->device < 64) { DevClock& k = g_clock[c->device]; std::lock_guard<std::mutex> l(k.mu); out->device_union_ms = k.unionMs; }
     return FB_OK;
 }
 
@@ -1092,6 +1103,15 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
     CK(cudaStreamSynchronize(c->stream));
     float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->ctr.device_ms += ms; c->ctr.kernel_launches += launches; c->ctr.d2h_bytes += (int64_t)outTotal;
+    if (c->device < 64) {
+        DevClock& k = g_clock[c->device]; std::lock_guard<std::mutex> l(k.mu);
+        float s0 = 0, s1 = 0;
+        if (k.epoch && cudaEventElapsedTime(&s0, k.epoch, c->ev0) == cudaSuccess && cudaEventElapsedTime(&s1, k.epoch, c->ev1) == cudaSuccess) {
+            const double b = std::max((double)s0, k.lastEnd);
+            if (s1 > b) k.unionMs += s1 - b;
+            k.lastEnd = std::max(k.lastEnd, (double)s1);
+        }
+    }
     c->ctr.placements_p1 = (int64_t)hc[0]; c->ctr.placements_p2 = (int64_t)hc[1]; c->ctr.base_terms = (int64_t)hc[2];
     c->ctr.lane_steps_p1 = (int64_t)hc[3]; c->ctr.lane_steps_p2 = (int64_t)hc[4];
     for (int i = 0; i < n; i++) {

@@ -30,12 +30,30 @@ class BatchQueue : public DeviceQueue {
 public:
     BatchQueue(fb_ctx* ctx, int workers) : ctx_(ctx), running_(workers) {}
     void submit(int gapIdx, const std::vector<ItemSpec>& items, std::vector<ItemResult>& results) override {
-        Req rq{gapIdx, &items, &results, false};
-        std::unique_lock<std::mutex> lk(mu_);
-        reqs_.push_back(&rq);
-        if ((int)reqs_.size() >= running_) flush(lk);
-        else cv_.wait(lk, [&] { return rq.done; });
-        if (failed_) throw std::runtime_error(err_);
+        Req rq{gapIdx, &items, {}, false};
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            reqs_.push_back(&rq);
+            if ((int)reqs_.size() >= running_) flush(lk);
+            else cv_.wait(lk, [&] { return rq.done; });
+            if (failed_) throw std::runtime_error(err_);
+        }
+        // every gap thread unpacks its own results (the arena stays valid until the next flush, which needs this thread to block again)
+        results.clear(); results.reserve(rq.outs.size());
+        for (const FbItemOut* h : rq.outs) {
+            ItemResult res; const unsigned char* b = (const unsigned char*)h;
+            res.calls = h->calls; res.compCount = h->comp_count; res.flags = h->flags; res.nReads = h->n_reads;
+            res.candLen = h->cand_len; res.nSlots = h->n_slots; res.placements = h->placements;
+            const size_t n = (size_t)h->n_slots * h->n_reads;
+            const double* p1 = (const double*)(b + h->off_p1max); res.p1max.assign(p1, p1 + n);
+            const double* p2 = (const double*)(b + h->off_p2max); res.p2max.assign(p2, p2 + n);
+            const int32_t* ps = (const int32_t*)(b + h->off_pos2); res.pos2.assign(ps, ps + n);
+            res.soft.assign(b + h->off_soft, b + h->off_soft + h->cand_len);
+            res.hard.assign(b + h->off_hard, b + h->off_hard + h->cand_len);
+            const int32_t* cv = (const int32_t*)(b + h->off_cov); res.cov.assign(cv, cv + h->cand_len);
+            if (h->off_counts >= 0) { const double* c = (const double*)(b + h->off_counts); res.counts.assign(c, c + (size_t)5 * h->cand_len); }
+            results.push_back(std::move(res));
+        }
     }
     void workerExit() {
         std::unique_lock<std::mutex> lk(mu_);
@@ -47,7 +65,7 @@ public:
     double copySeconds() const { return tCopy_; }
 
 private:
-    struct Req { int gap; const std::vector<ItemSpec>* items; std::vector<ItemResult>* results; bool done; };
+    struct Req { int gap; const std::vector<ItemSpec>* items; std::vector<const FbItemOut*> outs; bool done; };
     void flush(std::unique_lock<std::mutex>&) {
         std::vector<Req*> batch; batch.swap(reqs_);
         std::vector<FbWorkItem> wi;
@@ -66,24 +84,9 @@ private:
         if (st != FB_OK) { failed_ = true; err_ = std::string("fb_em_run failed: ") + fb_last_error(ctx_); }
         size_t k = 0;
         for (Req* r : batch) {
-            r->results->clear();
-            for (size_t i = 0; i < r->items->size(); i++, k++) {
-                ItemResult res;
-                if (!failed_) {
-                    const FbItemOut* h = outs[k]; const unsigned char* b = (const unsigned char*)h;
-                    res.calls = h->calls; res.compCount = h->comp_count; res.flags = h->flags; res.nReads = h->n_reads;
-                    res.candLen = h->cand_len; res.nSlots = h->n_slots; res.placements = h->placements;
-                    const size_t n = (size_t)h->n_slots * h->n_reads;
-                    const double* p1 = (const double*)(b + h->off_p1max); res.p1max.assign(p1, p1 + n);
-                    const double* p2 = (const double*)(b + h->off_p2max); res.p2max.assign(p2, p2 + n);
-                    const int32_t* ps = (const int32_t*)(b + h->off_pos2); res.pos2.assign(ps, ps + n);
-                    res.soft.assign(b + h->off_soft, b + h->off_soft + h->cand_len);
-                    res.hard.assign(b + h->off_hard, b + h->off_hard + h->cand_len);
-                    const int32_t* cv = (const int32_t*)(b + h->off_cov); res.cov.assign(cv, cv + h->cand_len);
-                    if (h->off_counts >= 0) { const double* c = (const double*)(b + h->off_counts); res.counts.assign(c, c + (size_t)5 * h->cand_len); }
-                }
-                r->results->push_back(std::move(res));
-            }
+            r->outs.clear();
+            if (!failed_) r->outs.assign(outs.begin() + k, outs.begin() + k + r->items->size());
+            k += r->items->size();
             r->done = true;
         }
         tCopy_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - c1).count();
@@ -116,12 +119,37 @@ static void parallelFor(int n, int threads, F f) {
     for (auto& t : th) t.join();
 }
 
+// Engine contexts survive fb_fillgaps_main: an in-process caller (one FillGaps call per pipeline iteration) pays stream /
+// buffer / pinned-arena creation once per (device, lane).  Leaked on purpose at process exit.
+struct CtxPool { std::mutex mu; std::vector<std::pair<int, fb_ctx*>> idle; };
+static CtxPool& ctxPool() { static CtxPool* p = new CtxPool; return *p; }
+static fb_ctx* acquireCtx(int device, std::string& err) {
+    {
+        CtxPool& P = ctxPool(); std::lock_guard<std::mutex> l(P.mu);
+        for (size_t i = 0; i < P.idle.size(); i++) if (P.idle[i].first == device) { fb_ctx* c = P.idle[i].second; P.idle.erase(P.idle.begin() + i); return c; }
+    }
+    fb_ctx* ctx = nullptr;
+    if (fb_ctx_create(device, &ctx) != FB_OK || !ctx) {
+        err = std::string("fb_ctx_create failed on device ") + std::to_string(device) + ": " + (ctx ? fb_last_error(ctx) : "no context");
+        if (ctx) fb_ctx_destroy(ctx);
+        return nullptr;
+    }
+    return ctx;
+}
+static void releaseCtx(int device, fb_ctx* ctx) { CtxPool& P = ctxPool(); std::lock_guard<std::mutex> l(P.mu); P.idle.emplace_back(device, ctx); }
+
 static std::vector<int> visibleDevices() {
     std::vector<int> d;
     const char* e = getenv("FIGBIRD_GPUS");
     if (e && *e) { for (const char* p = e; *p;) { d.push_back(atoi(p)); while (*p && *p != ',') p++; if (*p) p++; } }
     if (d.empty()) d.push_back(0);
-    return d;
+    // lanes: independent (context, batch queue, gap threads) groups on one GPU, so that the host replay of one group
+    // overlaps the kernels of the other
+    int lanes = 2;
+    if (const char* l = getenv("FIGBIRD_LANES")) lanes = std::max(1, atoi(l));
+    std::vector<int> out;
+    for (int x : d) for (int i = 0; i < lanes; i++) out.push_back(x);
+    return out;
 }
 
 struct RunStats { double tLoad = 0, tModel = 0, tPrep = 0, tFill = 0, tWrite = 0, tEngine = 0, tCopy = 0, tCtx = 0, tWorkers = 0, cpuWorkers = 0; int64_t refPlacements = 0; FbCounters dev{}; int64_t ticks = 0; };
@@ -140,10 +168,19 @@ int fillgapsMain(int argc, const char* const* argv) {
     Scaffolds sc;
     if (!loadScaffolds(a.draft, sc)) { printf("Can't open contig file\n"); return 1; }
     auto t1 = clk::now();
-    Model model; std::string err;
-    if (!learnModel(a, sc, model, err)) { printf("%s\n", err.c_str()); return 1; }
-    auto t2 = clk::now();
-    if (getenv("FIGBIRD_DUMP_MODEL")) {
+    // the model is learned on its own thread while the per-gap inputs are read, encoded and uploaded; nothing before the
+    // first engine call needs it
+    Model model; std::string err; bool modelOk = false; double modelSecs = 0;
+    std::mutex modelMu; std::condition_variable modelCv; bool modelDone = false;
+    std::thread modelThread([&] {
+        auto m0 = clk::now();
+        bool ok = learnModel(a, sc, model, err);
+        std::lock_guard<std::mutex> l(modelMu); modelOk = ok; modelSecs = secs(m0, clk::now()); modelDone = true; modelCv.notify_all();
+    });
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } modelJoiner{modelThread};
+    auto waitModel = [&]() -> bool { std::unique_lock<std::mutex> l(modelMu); modelCv.wait(l, [&] { return modelDone; }); return modelOk; };
+    auto t2 = t1;
+    if (getenv("FIGBIRD_DUMP_MODEL") && waitModel()) {
         FILE* fm = fopen(getenv("FIGBIRD_DUMP_MODEL"), "w");
         if (fm) {
             fprintf(fm, "mean %.17g leftSD %.17g rightSD %.17g tmin %d tmax %d cutoff %d maxins %d maxread %d\n", model.insertSizeMean, model.leftSD, model.rightSD,
@@ -193,14 +230,9 @@ int fillgapsMain(int argc, const char* const* argv) {
         const std::vector<int>& mine = shard[d];
         if (mine.empty()) return;
         auto d0 = clk::now();
-        fb_ctx* ctx = nullptr;
-        if (fb_ctx_create(devs[d], &ctx) != FB_OK || !ctx) { devErr[d] = std::string("fb_ctx_create failed on device ") + std::to_string(devs[d]) + ": " + (ctx ? fb_last_error(ctx) : "no context"); if (ctx) fb_ctx_destroy(ctx); return; }
-        FbModel fm{};
-        fm.max_read_len = model.maxReadLength; fm.err_pos = model.errorPosDist.data(); fm.ins_pos = model.inPosDist.data(); fm.del_pos = model.delPosDist.data();
-        for (int i = 0; i < 5; i++) for (int j = 0; j < 5; j++) fm.err_type[i * 5 + j] = model.errorTypeProbs[i][j];
-        fm.n_insert = model.maxInsertSize; fm.insert_pdf = model.insertPdfSmoothed.data();
-        fm.insert_min = model.insertThresholdMin; fm.insert_max = model.insertThresholdMax; fm.prob_cutoff = model.gapProbCutOff;
-        if (fb_model_upload(ctx, &fm) != FB_OK) { devErr[d] = std::string("fb_model_upload: ") + fb_last_error(ctx); fb_ctx_destroy(ctx); return; }
+        fb_ctx* ctx = acquireCtx(devs[d], devErr[d]);
+        if (!ctx) return;
+        FbCounters ctr0{}; fb_get_counters(ctx, &ctr0);
         // batch of this shard
         std::vector<FbGap> fg; std::vector<int32_t> rlen, rmate, pileL, pileR; std::vector<int64_t> roff; std::vector<uint8_t> rfl, rjlo, rjcut, codes, flank;
         for (int g : mine) {
@@ -227,6 +259,13 @@ int fillgapsMain(int argc, const char* const* argv) {
         B.read_flags = rfl.data(); B.read_jlo = rjlo.data(); B.read_jcut = rjcut.data(); B.n_codes = (int64_t)codes.size(); B.read_codes = codes.data();
         B.n_flank = (int64_t)flank.size(); B.flank_codes = flank.data(); B.n_pile_rows = (int64_t)(pileL.size() / 4); B.pile_left = pileL.data(); B.pile_right = pileR.data();
         if (fb_batch_upload(ctx, &B) != FB_OK) { devErr[d] = std::string("fb_batch_upload: ") + fb_last_error(ctx); fb_ctx_destroy(ctx); return; }
+        if (!waitModel()) { releaseCtx(devs[d], ctx); return; }      // reported by the main thread
+        FbModel fm{};
+        fm.max_read_len = model.maxReadLength; fm.err_pos = model.errorPosDist.data(); fm.ins_pos = model.inPosDist.data(); fm.del_pos = model.delPosDist.data();
+        for (int i = 0; i < 5; i++) for (int j = 0; j < 5; j++) fm.err_type[i * 5 + j] = model.errorTypeProbs[i][j];
+        fm.n_insert = model.maxInsertSize; fm.insert_pdf = model.insertPdfSmoothed.data();
+        fm.insert_min = model.insertThresholdMin; fm.insert_max = model.insertThresholdMax; fm.prob_cutoff = model.gapProbCutOff;
+        if (fb_model_upload(ctx, &fm) != FB_OK) { devErr[d] = std::string("fb_model_upload: ") + fb_last_error(ctx); fb_ctx_destroy(ctx); return; }
 
         auto d1 = clk::now();
         devCtx[d] = secs(d0, d1);
@@ -247,10 +286,18 @@ int fillgapsMain(int argc, const char* const* argv) {
         });
         for (auto& t : th) t.join();
         devWork[d] = secs(d1, clk::now()); devCpu[d] = cpuNs.load() * 1e-9;
-        fb_get_counters(ctx, &devCtr[d]); devTicks[d] = q.ticks(); devEng[d] = q.engineSeconds(); devCopy[d] = q.copySeconds();
-        fb_ctx_destroy(ctx);
+        {   // this run's share of the context's cumulative counters
+            FbCounters c1{}; fb_get_counters(ctx, &c1);
+            c1.placements_p1 -= ctr0.placements_p1; c1.placements_p2 -= ctr0.placements_p2; c1.base_terms -= ctr0.base_terms; c1.kernel_launches -= ctr0.kernel_launches;
+            c1.device_ms -= ctr0.device_ms; c1.h2d_bytes -= ctr0.h2d_bytes; c1.d2h_bytes -= ctr0.d2h_bytes; c1.lane_steps_p1 -= ctr0.lane_steps_p1; c1.lane_steps_p2 -= ctr0.lane_steps_p2;
+            c1.device_union_ms -= ctr0.device_union_ms;
+            devCtr[d] = c1;
+        }
+        devTicks[d] = q.ticks(); devEng[d] = q.engineSeconds(); devCopy[d] = q.copySeconds();
+        releaseCtx(devs[d], ctx);
     });
     for (auto& t : devThreads) t.join();
+    if (!waitModel()) { printf("%s\n", err.c_str()); return 1; }
     for (auto& e : devErr) if (!e.empty()) { fprintf(stderr, "figbird_b200: %s\n", e.c_str()); return 1; }
     auto t4 = clk::now();
 
@@ -262,11 +309,17 @@ int fillgapsMain(int argc, const char* const* argv) {
     }
     if (!writeFilledContigs(a.tmpDir, sc, gaps, results, totGaps)) { fprintf(stderr, "cannot write filledContigs.fa\n"); return 1; }
     auto t5 = clk::now();
-    rs.tLoad = secs(t0, t1); rs.tModel = secs(t1, t2); rs.tPrep = secs(t2, t3); rs.tFill = secs(t3, t4); rs.tWrite = secs(t4, t5);
+    rs.tLoad = secs(t0, t1); rs.tModel = modelSecs; rs.tPrep = secs(t2, t3); rs.tFill = secs(t3, t4); rs.tWrite = secs(t4, t5);
     for (auto& r : results) rs.refPlacements += r.refPlacements;
     for (int d = 0; d < nD; d++) {
         rs.dev.placements_p1 += devCtr[d].placements_p1; rs.dev.placements_p2 += devCtr[d].placements_p2; rs.dev.base_terms += devCtr[d].base_terms;
-        rs.dev.kernel_launches += devCtr[d].kernel_launches; rs.dev.device_ms = std::max(rs.dev.device_ms, devCtr[d].device_ms);
+        rs.dev.kernel_launches += devCtr[d].kernel_launches;
+        {   // lanes of one GPU overlap their kernels: the device time of a GPU is the union of its kernel intervals, which the
+            // engine tracks per physical device (same value in every lane of that GPU); across GPUs take the maximum
+            double u = devCtr[d].device_union_ms;
+            for (int e2 = 0; e2 < nD; e2++) if (devs[e2] == devs[d]) u = std::max(u, devCtr[e2].device_union_ms);
+            rs.dev.device_ms = std::max(rs.dev.device_ms, u > 0 ? u : devCtr[d].device_ms);
+        }
         rs.dev.h2d_bytes += devCtr[d].h2d_bytes; rs.dev.d2h_bytes += devCtr[d].d2h_bytes; rs.dev.lane_steps_p1 += devCtr[d].lane_steps_p1; rs.dev.lane_steps_p2 += devCtr[d].lane_steps_p2; rs.ticks += devTicks[d]; rs.tEngine = std::max(rs.tEngine, devEng[d]); rs.tCopy = std::max(rs.tCopy, devCopy[d]); rs.tCtx = std::max(rs.tCtx, devCtx[d]); rs.tWorkers = std::max(rs.tWorkers, devWork[d]); rs.cpuWorkers += devCpu[d];
     }
     if (const char* mp = getenv("FIGBIRD_METRICS")) {

@@ -161,6 +161,8 @@ typedef struct {
     int64_t lane_steps_p1;      /* pass-1 gap-row terms actually executed (warp steps x 32 lanes): flank terms come from the
                                    per-gap cache and inadmissible offsets are never visited, so this is below base_terms */
     int64_t lane_steps_p2;      /* pass-2 terms actually executed (pruned against the pass-1 winner) */
+    double device_union_ms;     /* union of the kernel intervals of ALL contexts of this process on this physical device
+                                   (contexts that share a GPU overlap their kernels; sum of device_ms would double count) */
 } FbCounters;
 
 fb_status fb_ctx_create(int32_t device, fb_ctx** out);
