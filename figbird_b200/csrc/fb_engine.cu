@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(128) fb_flank_kernel(const Params prm, int nRe
 }
 
 template <bool TSMEM>
-__global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Params prm, const int* __restrict__ order, const int smemBytes) {
+__global__ void __launch_bounds__(kThreads, TSMEM ? 3 : 1) fb_em_kernel(const Params prm, const int* __restrict__ order, const int smemBytes) {
     const DevItem it = prm.items[order[blockIdx.x]];
     const DevGap g = prm.gaps[it.gap];
     const DevModel& m = prm.m;
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
     const int S = pl.S, rows = pl.rows, mlp = pl.maxLenPad;
 
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ int s_comp, s_same, s_flags, s_q1;
+    __shared__ int s_comp, s_same, s_flags, s_q1, s_next1, s_next2;
     __shared__ int s_scan[3][kThreads];
     __shared__ unsigned long long s_lane1, s_lane2, s_terms;
 
@@ -446,7 +446,11 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
             q1 = chunkEnd(q0);
             if (!singleChunk) { stageReads(q0, q1); __syncthreads(); }
             const int nq = q1 - q0;
-            // exact product at the offset that won pass 1: every other offset only has to beat it
+            // exact product at the offset that won pass 1: every other offset only has to beat it.  EM items additionally
+            // stop at the accept threshold: a read whose best product stays below it is rejected whatever the exact value
+            // (FbItemOut: p2max / pos2 of rejected reads are unspecified below the threshold); HARD items stay exact.
+            const double floorP = (vote && m.prunable && m.accept_min_p < 1e300) ? m.accept_min_p : 0.0;
+            if (tid == 0) s_next2 = 0;
             for (int ql = tid; ql < nq; ql += kThreads) {
                 const RMeta r = RM[ql];
                 double thr = 0.0;
@@ -467,14 +471,19 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
             }
             __syncthreads();
             const int units = RM[nq].u2;
-            for (int u = warp; u < units; u += kWarps) {
+            for (;;) {
+                int u = 0;
+                if (lane == 0) u = atomicAdd(&s_next2, 1);
+                u = __shfl_sync(0xffffffffu, u, 0);
+                if (u >= units) break;
                 const int ql = findRead(true, u);
                 const RMeta r = RM[ql];
                 const int ch = u - r.u2;
                 const int len = r.packed & 0xff, jlo = (r.packed >> 8) & 0xff, jhi = (r.packed >> 16) & 0xff;
                 const int xlo = r.xlo, n = r.n;
-                const double thr = THR[ql];
-                const int x1 = (thr > 0.0) ? r.x1 : INT_MIN;      // known exactly: not walked again
+                const double thrX = THR[ql];
+                const int x1 = (thrX > 0.0) ? r.x1 : INT_MIN;      // known exactly: not walked again
+                const double thr = fmax(thrX, floorP);             // running products below this cannot matter
                 const int ia = ch * 64 + lane, ib = ia + 32;
                 const int xa = xlo + ia, xb = xlo + ib;
                 const bool ina = ia < n, inb = ib < n;
@@ -502,8 +511,8 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
                     }
                     if (lane == 0) atomicAdd(&s_lane2, (unsigned long long)steps * 64ull);
                 }
-                if (ina) W[r.wrel + ia] = acta ? pa : thr;
-                if (inb) W[r.wrel + ib] = actb ? pb : thr;
+                if (ina) W[r.wrel + ia] = acta ? pa : thrX;
+                if (inb) W[r.wrel + ib] = actb ? pb : thrX;
             }
             __syncthreads();
             // first maximum over ascending offsets (strict >), accept test, unit votes (Figbird.cpp:3787-3912)
@@ -555,6 +564,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
             const bool extra = emDone;
             const int slot = (it.flags & FB_FLAG_RECORD_ALL) ? call : 0;
             for (int i = tid; i < 5 * Lg; i += kThreads) { C[i] = 0.0; NC[i] = 0; }
+            if (tid == 0) s_next1 = 0;
             __syncthreads();
             // ================= pass 1 (Figbird.cpp:3082-3263, 3530-3689) =================
             for (int q0 = 0, q1; q0 < R; q0 = q1) {
@@ -563,7 +573,11 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
                 const int nq = q1 - q0;
                 // ---- gap-row products of every admissible placement: cyclic diagonal walk
                 const int units = (Lg > 0) ? RM[nq].u1 : 0;
-                for (int u = warp; u < units; u += kWarps) {
+                for (;;) {
+                    int u = 0;
+                    if (lane == 0) u = atomicAdd(&s_next1, 1);
+                    u = __shfl_sync(0xffffffffu, u, 0);
+                    if (u >= units) break;
                     const int ql = findRead(false, u);
                     const RMeta r = RM[ql];
                     const int uu = u - r.u1;
@@ -587,45 +601,58 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
                     const unsigned char* rc = RC + ql * mlp;
                     const double* me = ME; int kstep = 1, kb = 0;
                     if ((r.packed >> 24) & FB_READ_REVERSE) { kb = len - 1; kstep = -1; }
-                    double acc = 1.0;
+                    double acc = 1.0, save = 1.0;
+                    const bool oneWrap = (je - js) <= Lg;     // a lane re-enters row 0 at most once: keep the first product in a register
                     auto mul = [&](const double2 v, double e) { acc = __dmul_rn(acc, __fma_rn(e, v.y, v.x)); };
-                    auto wrap = [&](int j) {
+                    auto wrap1 = [&](int j) { const bool w = (j == jw); save = w ? acc : save; acc = w ? 1.0 : acc; };
+                    auto wrapN = [&](int j) {
                         if (j == jw) {      // the walk re-enters gap row 0: the running product belongs to placement x0cur
                             if (active && (unsigned)(x0cur - xlo) < (unsigned)n) Wq[x0cur - xlo] = acc;
                             acc = 1.0; x0cur -= Lg; jw += Lg;
                         }
                     };
-                    // read bases [j, stop): CHECK = some lane of the warp may wrap in this stretch
-                    auto run = [&](auto CHECK, int& j, int stop) {
-                        for (; j < stop && (j & 3); j++) { if (CHECK.value) wrap(j); mul(ptr[rc[j] * S + j], me[kb + kstep * j]); }
+                    // read bases [j, stop): MODE 0 = no lane wraps in this stretch, 1 = single-wrap lanes, 2 = general
+                    auto run = [&](auto MODE, int& j, int stop) {
+                        auto wr = [&](int jj) { if (MODE.value == 1) wrap1(jj); else if (MODE.value == 2) wrapN(jj); };
+                        for (; j < stop && (j & 3); j++) { wr(j); mul(ptr[rc[j] * S + j], me[kb + kstep * j]); }
                         for (; j + 4 <= stop; j += 4) {
                             const unsigned cw = *(const unsigned*)(rc + j);
                             const double2* pj = ptr + j;
                             const double2 v0 = pj[(cw & 0xff) * S], v1 = pj[((cw >> 8) & 0xff) * S + 1], v2 = pj[((cw >> 16) & 0xff) * S + 2], v3 = pj[(cw >> 24) * S + 3];
                             const double e0 = me[kb + kstep * j], e1 = me[kb + kstep * (j + 1)], e2 = me[kb + kstep * (j + 2)], e3 = me[kb + kstep * (j + 3)];
-                            if (CHECK.value) wrap(j);
-                            mul(v0, e0);
-                            if (CHECK.value) wrap(j + 1);
-                            mul(v1, e1);
-                            if (CHECK.value) wrap(j + 2);
-                            mul(v2, e2);
-                            if (CHECK.value) wrap(j + 3);
-                            mul(v3, e3);
+                            wr(j); mul(v0, e0);
+                            wr(j + 1); mul(v1, e1);
+                            wr(j + 2); mul(v2, e2);
+                            wr(j + 3); mul(v3, e3);
                         }
-                        for (; j < stop; j++) { if (CHECK.value) wrap(j); mul(ptr[rc[j] * S + j], me[kb + kstep * j]); }
+                        for (; j < stop; j++) { wr(j); mul(ptr[rc[j] * S + j], me[kb + kstep * j]); }
                     };
                     // lanes hold consecutive diagonals, so their wrap points fill a window of at most 32 consecutive read bases per period
                     int wmin = __reduce_min_sync(0xffffffffu, jw), wmax = __reduce_max_sync(0xffffffffu, jw);
                     int j = js;
-                    while (j < je) {
-                        run(std::false_type(), j, min(je, wmin));
-                        run(std::true_type(), j, min(je, wmax + 1));
-                        wmin += Lg; wmax += Lg;
+                    if (oneWrap) {
+                        run(std::integral_constant<int, 0>(), j, min(je, wmin));
+                        run(std::integral_constant<int, 1>(), j, min(je, wmax + 1));
+                        run(std::integral_constant<int, 0>(), j, je);
+                        if (active) {
+                            const bool wrapped = jw < je;
+                            if (wrapped) {
+                                if ((unsigned)(x0cur - xlo) < (unsigned)n) Wq[x0cur - xlo] = save;
+                                if ((unsigned)(x0cur - Lg - xlo) < (unsigned)n) Wq[x0cur - Lg - xlo] = acc;
+                            } else if ((unsigned)(x0cur - xlo) < (unsigned)n) Wq[x0cur - xlo] = acc;
+                        }
+                    } else {
+                        while (j < je) {
+                            run(std::integral_constant<int, 0>(), j, min(je, wmin));
+                            run(std::integral_constant<int, 2>(), j, min(je, wmax + 1));
+                            wmin += Lg; wmax += Lg;
+                        }
+                        if (active && (unsigned)(x0cur - xlo) < (unsigned)n) Wq[x0cur - xlo] = acc;
                     }
-                    if (active && (unsigned)(x0cur - xlo) < (unsigned)n) Wq[x0cur - xlo] = acc;
                     if (lane == 0) atomicAdd(&s_lane1, (unsigned long long)(je - js) * 32ull);
                 }
                 __syncthreads();
+                if (tid == 0) s_next1 = 0;      // every warp has left the unit loop; the next one starts after further barriers
                 // ---- finish every placement: insert pdf x left-flank product x gap product x right-flank product,
                 //      per-read maximum (value and offset), soft weight in place
                 for (int ql = warp; ql < nq; ql += kWarps) {
@@ -690,14 +717,26 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
                         auto ld = [&](int i) -> double { return ((unsigned)i < (unsigned)n) ? wr[i] : 0.0; };
                         int i0 = x - ja - xlo;                 // weight index of row x at read base ja; row x+b: i0 + b
                         double w0 = ld(i0), w1 = ld(i0 + 1), w2 = ld(i0 + 2), w3 = ld(i0 + 3);
-                        for (int j = ja; j <= jb; j++) {
-                            switch (rc[j]) {
-                                case 0: a[0][0] = __dadd_rn(a[0][0], w0); a[1][0] = __dadd_rn(a[1][0], w1); a[2][0] = __dadd_rn(a[2][0], w2); a[3][0] = __dadd_rn(a[3][0], w3); break;
-                                case 1: a[0][1] = __dadd_rn(a[0][1], w0); a[1][1] = __dadd_rn(a[1][1], w1); a[2][1] = __dadd_rn(a[2][1], w2); a[3][1] = __dadd_rn(a[3][1], w3); break;
-                                case 2: a[0][2] = __dadd_rn(a[0][2], w0); a[1][2] = __dadd_rn(a[1][2], w1); a[2][2] = __dadd_rn(a[2][2], w2); a[3][2] = __dadd_rn(a[3][2], w3); break;
-                                case 3: a[0][3] = __dadd_rn(a[0][3], w0); a[1][3] = __dadd_rn(a[1][3], w1); a[2][3] = __dadd_rn(a[2][3], w2); a[3][3] = __dadd_rn(a[3][3], w3); break;
-                                default: a[0][4] = __dadd_rn(a[0][4], w0); a[1][4] = __dadd_rn(a[1][4], w1); a[2][4] = __dadd_rn(a[2][4], w2); a[3][4] = __dadd_rn(a[3][4], w3);
+                        auto add = [&](int c, double v0, double v1, double v2, double v3) {
+                            switch (c) {
+                                case 0: a[0][0] = __dadd_rn(a[0][0], v0); a[1][0] = __dadd_rn(a[1][0], v1); a[2][0] = __dadd_rn(a[2][0], v2); a[3][0] = __dadd_rn(a[3][0], v3); break;
+                                case 1: a[0][1] = __dadd_rn(a[0][1], v0); a[1][1] = __dadd_rn(a[1][1], v1); a[2][1] = __dadd_rn(a[2][1], v2); a[3][1] = __dadd_rn(a[3][1], v3); break;
+                                case 2: a[0][2] = __dadd_rn(a[0][2], v0); a[1][2] = __dadd_rn(a[1][2], v1); a[2][2] = __dadd_rn(a[2][2], v2); a[3][2] = __dadd_rn(a[3][2], v3); break;
+                                case 3: a[0][3] = __dadd_rn(a[0][3], v0); a[1][3] = __dadd_rn(a[1][3], v1); a[2][3] = __dadd_rn(a[2][3], v2); a[3][3] = __dadd_rn(a[3][3], v3); break;
+                                default: a[0][4] = __dadd_rn(a[0][4], v0); a[1][4] = __dadd_rn(a[1][4], v1); a[2][4] = __dadd_rn(a[2][4], v2); a[3][4] = __dadd_rn(a[3][4], v3);
                             }
+                        };
+                        int j = ja;
+                        for (; j + 3 <= jb; j += 4) {       // four read bases per trip: the window of weights rotates through the names
+                            const double n0 = ld(i0 - 1), n1 = ld(i0 - 2), n2 = ld(i0 - 3), n3 = ld(i0 - 4);
+                            add(rc[j], w0, w1, w2, w3);
+                            add(rc[j + 1], n0, w0, w1, w2);
+                            add(rc[j + 2], n1, n0, w0, w1);
+                            add(rc[j + 3], n2, n1, n0, w0);
+                            w3 = n0; w2 = n1; w1 = n2; w0 = n3; i0 -= 4;
+                        }
+                        for (; j <= jb; j++) {
+                            add(rc[j], w0, w1, w2, w3);
                             i0--;
                             w3 = w2; w2 = w1; w1 = w0; w0 = ld(i0);
                         }

@@ -143,8 +143,10 @@ typedef struct {
     int32_t n_slots;            /* recorded calls: `calls` with RECORD_ALL, else 1 (the last) */
     int64_t placements;         /* (read, admissible offset) pairs scored in pass 1, summed over calls */
     int64_t off_p1max;          /* double[n_slots][n_reads] largest pass-1 product per read; -1 = no admissible offset */
-    int64_t off_p2max;          /* double[n_slots][n_reads] largest pass-2 product per read; -1 = none */
-    int64_t off_pos2;           /* int32 [n_slots][n_reads] x0 of the first offset reaching p2max */
+    int64_t off_p2max;          /* double[n_slots][n_reads] largest pass-2 product per read; -1 = none.  EM items: exact whenever the
+                                   read is accepted (-log10(p) < prob_cutoff, Figbird.cpp:3474,3852); for a rejected read only
+                                   "below the accept threshold" is guaranteed (the scan stops early).  HARD items: always exact */
+    int64_t off_pos2;           /* int32 [n_slots][n_reads] x0 of the first offset reaching p2max (same validity as p2max) */
     int64_t off_soft;           /* uint8 [cand_len] computeSequence(0,0) codes after the last call (4 = N) */
     int64_t off_hard;           /* uint8 [cand_len] computeSequence(1,1) codes (unmapped mode) */
     int64_t off_cov;            /* int32 [cand_len] gap_coverage (unmapped mode) */

@@ -48,12 +48,12 @@ bool init() {
 long g_mismatch = 0, g_items = 0;
 }  // namespace
 
-struct fb_ctx { fb_ctx* d; fb_ctx* o; std::string err; };
+struct fb_ctx { fb_ctx* d; fb_ctx* o; std::string err; int cutoff = 0; };
 
 extern "C" const char* fb_engine_name(void) { return "dual(cuda-sm100a|oracle-cpu)"; }
 extern "C" fb_status fb_ctx_create(int32_t device, fb_ctx** out) {
     if (!init()) return FB_ERR_STATE;
-    fb_ctx* c = new fb_ctx{nullptr, nullptr, ""};
+    fb_ctx* c = new fb_ctx(); c->d = nullptr; c->o = nullptr;
     *out = c;
     fb_status s = dev().ctx_create(device, &c->d);
     if (s != FB_OK) { c->err = "device engine: ctx_create failed"; return s; }
@@ -67,7 +67,7 @@ extern "C" void fb_ctx_destroy(fb_ctx* c) {
     delete c;
 }
 extern "C" const char* fb_last_error(const fb_ctx* c) { return c ? (c->err.empty() ? dev().last_error(c->d) : c->err.c_str()) : "null"; }
-extern "C" fb_status fb_model_upload(fb_ctx* c, const FbModel* m) { fb_status s = dev().model_upload(c->d, m); return s ? s : ora().model_upload(c->o, m); }
+extern "C" fb_status fb_model_upload(fb_ctx* c, const FbModel* m) { c->cutoff = m->prob_cutoff; fb_status s = dev().model_upload(c->d, m); return s ? s : ora().model_upload(c->o, m); }
 extern "C" fb_status fb_batch_upload(fb_ctx* c, const FbGapBatch* b) { fb_status s = dev().batch_upload(c->d, b); return s ? s : ora().batch_upload(c->o, b); }
 extern "C" fb_status fb_get_counters(const fb_ctx* c, FbCounters* o) { return dev().get_counters(c->d, o); }
 extern "C" fb_status fb_microbench_fp64(fb_ctx* c, double* o) { return dev().microbench(c->d, o); }
@@ -98,9 +98,16 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items_in, int32_t n,
             const double* ap2 = (const double*)(a + A->off_p2max); const double* bp2 = (const double*)(b + B->off_p2max);
             const int32_t* aps = (const int32_t*)(a + A->off_pos2); const int32_t* bps = (const int32_t*)(b + B->off_pos2);
             const double* ap1 = (const double*)(a + A->off_p1max); const double* bp1 = (const double*)(b + B->off_p1max);
+            // EM items: p2max / pos2 are guaranteed only for accepted reads; a rejected read must be rejected by both engines
+            const bool em = items[i].kind == FB_ITEM_EM; const double cut = (double)c->cutoff;
+            auto accepted = [&](double p) { return p > 0 && -log10(p) < cut; };
             for (int k = 0; k < slots * R; k++) {
+                if (em && !accepted(ap2[k])) {
+                    if (accepted(bp2[k])) { char buf[200]; snprintf(buf, sizeof buf, " accept[%d] oracle %.17g (rejected) device %.17g", k, ap2[k], bp2[k]); why += buf; break; }
+                } else {
                 if (ap2[k] != bp2[k]) { char buf[200]; snprintf(buf, sizeof buf, " p2max[%d] oracle %.17g pos %d device %.17g pos %d", k, ap2[k], aps[k], bp2[k], bps[k]); why += buf; break; }
                 if (aps[k] != bps[k]) { why += " pos2[" + std::to_string(k) + "]"; break; }
+                }
                 if ((ap1[k] > 0) != (bp1[k] > 0) || (ap1[k] > 0 && fabs(ap1[k] - bp1[k]) > 1e-9 * ap1[k])) { char buf[200]; snprintf(buf, sizeof buf, " p1max[%d] oracle %.17g device %.17g", k, ap1[k], bp1[k]); why += buf; break; }
             }
             if (memcmp(a + A->off_soft, b + B->off_soft, Lg)) {

@@ -84,21 +84,36 @@ def make_gap(rng, mode, true_len, og, L=100, n_reads=30, mu=200.0, sd=20.0, gap_
     return dict(gap_start=gap_start, mode=mode, orig_len=og, flank=flank, pile_left=pile_l, pile_right=pile_r, reads=reads, true_len=true_len)
 
 
-def compare_results(a, b, rtol_counts=1e-5):
-    """a: oracle result, b: device result (dicts of Engine.run).  Returns list of mismatch descriptions."""
+def compare_results(a, b, rtol_counts=1e-5, cutoff=None, hard=False):
+    """a: oracle result, b: device result (dicts of Engine.run).  Returns list of mismatch descriptions.
+    cutoff: prob_cutoff of the model.  For EM items the engine guarantees p2max / pos2 only for accepted reads
+    (-log10(p) < cutoff); a rejected read must be rejected by both (include/figbird_b200.h, FbItemOut)."""
     bad = []
     for k in ("calls", "comp_count", "flags", "n_reads", "cand_len", "placements"):
         if a[k] != b[k]:
             bad.append("%s: %r vs %r" % (k, a[k], b[k]))
     ns = a["calls"] if a["n_slots"] > 1 else 1
+    acc = None
+    if cutoff is not None and not hard:
+        def accepted(p):
+            p = np.asarray(p, dtype=np.float64)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                return (p > 0) & (-np.log10(np.where(p > 0, p, 1.0)) < cutoff)
+        acc = accepted(a["p2max"][:ns])
+        if not np.array_equal(acc, accepted(b["p2max"][:ns])):
+            bad.append("accept decisions differ")
     for k in ("pos2", "soft", "hard", "cov"):
         x, y = a[k], b[k]
         if k == "pos2":
             x, y = x[:ns], y[:ns]
+            if acc is not None:
+                x, y = np.where(acc, x, 0), np.where(acc, y, 0)
         if not np.array_equal(x, y):
             bad.append("%s differs at %s" % (k, np.argwhere(np.asarray(x) != np.asarray(y))[:5].tolist()))
     for k in ("p1max", "p2max"):
         x, y = a[k][:ns], b[k][:ns]
+        if k == "p2max" and acc is not None:
+            x, y = np.where(acc, x, 0.0), np.where(acc, y, 0.0)
         if k == "p2max":
             # products of exact table entries in the same order: bit-exact
             if not np.array_equal(x, y):
