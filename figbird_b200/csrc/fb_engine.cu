@@ -52,7 +52,7 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxSmem = 200 * 1024;      // dynamic shared memory we opt in to (227 KB is the sm_100 limit)
 constexpr int kChunkWant = 72 * 1024;     // weights + read-code staging we ask for per CTA when the reads allow it
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(128) fb_flank_kernel(const Params prm, int nRe
 }
 
 template <bool TSMEM>
-__global__ void __launch_bounds__(kThreads, TSMEM ? 3 : 1) fb_em_kernel(const Params prm, const int* __restrict__ order, const int smemBytes) {
+__global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Params prm, const int* __restrict__ order, const int smemBytes) {
     const DevItem it = prm.items[order[blockIdx.x]];
     const DevGap g = prm.gaps[it.gap];
     const DevModel& m = prm.m;
@@ -554,9 +554,10 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 3 : 1) fb_em_kernel(const Pa
         const int maxCalls = it.max_rounds + ((it.flags & FB_FLAG_EXTRA_PASS) ? 1 : 0);
         bool emDone = it.max_rounds <= 0;
         const long long offLg = (long long)Lg - g.orig_len;
-        // gather geometry: a task = 4 consecutive gap rows x one part of the reads; parts are combined in order through
+        // gather geometry: a task = 2 or 4 consecutive gap rows x one part of the reads; parts are combined in order through
         // a scratch that aliases the row tables (dead between the walk and the M-step), so only when all reads are resident
-        const int nG = (Lg + 3) >> 2, tpp = (nG + 31) & ~31;
+        const int rowsPerThread = (Lg >= 3 * kThreads) ? 4 : 2;
+        const int nG = (Lg + rowsPerThread - 1) / rowsPerThread, tpp = (nG + 31) & ~31;
         int split = 1;
         if (singleChunk && Lg > 0) { split = kThreads / tpp; const int cap = (2 * S) / Lg; split = max(1, min(min(split, cap), 8)); }
         double* const GP = (double*)UT;
@@ -695,66 +696,95 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 3 : 1) fb_em_kernel(const Pa
                 // A thread owns 4 consecutive rows x..x+3 and one part of the reads; all lanes of a warp walk the same read
                 // base j (uniform code -> uniform branch), row x+b takes the weight of placement x+b-j: one new weight
                 // per step slides through four registers.
-                for (int idx = tid; idx < tpp * split; idx += kThreads) {
-                    const int s = idx / tpp, gi = idx - s * tpp;
-                    const int x = gi << 2;
-                    const int xw0 = (gi - lane) << 2, xw1 = min(Lg - 1, xw0 + 127);      // rows of this warp
-                    double a[4][5];
+                auto gather = [&](auto BB) {
+                    constexpr int B = BB.value;           // gap rows per thread
+                    for (int idx = tid; idx < tpp * split; idx += kThreads) {
+                        const int s = idx / tpp, gi = idx - s * tpp;
+                        const int x = gi * B;
+                        const int xw0 = (gi - lane) * B, xw1 = min(Lg - 1, xw0 + 32 * B - 1);      // rows of this warp
+                        double a[B][5];
 #pragma unroll
-                    for (int b = 0; b < 4; b++)
+                        for (int b = 0; b < B; b++)
 #pragma unroll
-                        for (int k = 0; k < 5; k++) a[b][k] = 0.0;
-                    if (xw0 < Lg) for (int ql = s; ql < nq; ql += split) {
-                        const RMeta r = RM[ql];
-                        if (r.n <= 0) continue;
-                        const int len = r.packed & 0xff;
-                        const int xlo = r.xlo, n = r.n;
-                        // placement x0 = row - j in [xlo, xlo + n)  <=>  j in [row - xlo - n + 1, row - xlo]
-                        const int ja = max(0, xw0 - xlo - n + 1), jb = min(len - 1, xw1 - xlo);
-                        if (ja > jb) continue;
-                        const unsigned char* rc = RC + ql * mlp;
-                        const double* wr = W + r.wrel;
-                        auto ld = [&](int i) -> double { return ((unsigned)i < (unsigned)n) ? wr[i] : 0.0; };
-                        int i0 = x - ja - xlo;                 // weight index of row x at read base ja; row x+b: i0 + b
-                        double w0 = ld(i0), w1 = ld(i0 + 1), w2 = ld(i0 + 2), w3 = ld(i0 + 3);
-                        auto add = [&](int c, double v0, double v1, double v2, double v3) {
-                            switch (c) {
-                                case 0: a[0][0] = __dadd_rn(a[0][0], v0); a[1][0] = __dadd_rn(a[1][0], v1); a[2][0] = __dadd_rn(a[2][0], v2); a[3][0] = __dadd_rn(a[3][0], v3); break;
-                                case 1: a[0][1] = __dadd_rn(a[0][1], v0); a[1][1] = __dadd_rn(a[1][1], v1); a[2][1] = __dadd_rn(a[2][1], v2); a[3][1] = __dadd_rn(a[3][1], v3); break;
-                                case 2: a[0][2] = __dadd_rn(a[0][2], v0); a[1][2] = __dadd_rn(a[1][2], v1); a[2][2] = __dadd_rn(a[2][2], v2); a[3][2] = __dadd_rn(a[3][2], v3); break;
-                                case 3: a[0][3] = __dadd_rn(a[0][3], v0); a[1][3] = __dadd_rn(a[1][3], v1); a[2][3] = __dadd_rn(a[2][3], v2); a[3][3] = __dadd_rn(a[3][3], v3); break;
-                                default: a[0][4] = __dadd_rn(a[0][4], v0); a[1][4] = __dadd_rn(a[1][4], v1); a[2][4] = __dadd_rn(a[2][4], v2); a[3][4] = __dadd_rn(a[3][4], v3);
+                            for (int k = 0; k < 5; k++) a[b][k] = 0.0;
+                        if (xw0 < Lg) for (int ql = s; ql < nq; ql += split) {
+                            const RMeta r = RM[ql];
+                            if (r.n <= 0) continue;
+                            const int len = r.packed & 0xff;
+                            const int xlo = r.xlo, n = r.n;
+                            // placement x0 = row - j in [xlo, xlo + n)  <=>  j in [row - xlo - n + 1, row - xlo]
+                            const int ja = max(0, xw0 - xlo - n + 1), jb = min(len - 1, xw1 - xlo);
+                            if (ja > jb) continue;
+                            const unsigned char* rc = RC + ql * mlp;
+                            const double* wr = W + r.wrel;
+                            auto ld = [&](int i) -> double { return ((unsigned)i < (unsigned)n) ? wr[i] : 0.0; };
+                            int i0 = x - ja - xlo;                 // weight index of row x at read base ja; row x+b: i0 + b
+                            double w[B];
+#pragma unroll
+                            for (int b = 0; b < B; b++) w[b] = ld(i0 + b);
+                            auto add = [&](int c, const double (&v)[B]) {
+                                switch (c) {
+                                    case 0:
+#pragma unroll
+                                        for (int b = 0; b < B; b++) a[b][0] = __dadd_rn(a[b][0], v[b]);
+                                        break;
+                                    case 1:
+#pragma unroll
+                                        for (int b = 0; b < B; b++) a[b][1] = __dadd_rn(a[b][1], v[b]);
+                                        break;
+                                    case 2:
+#pragma unroll
+                                        for (int b = 0; b < B; b++) a[b][2] = __dadd_rn(a[b][2], v[b]);
+                                        break;
+                                    case 3:
+#pragma unroll
+                                        for (int b = 0; b < B; b++) a[b][3] = __dadd_rn(a[b][3], v[b]);
+                                        break;
+                                    default:
+#pragma unroll
+                                        for (int b = 0; b < B; b++) a[b][4] = __dadd_rn(a[b][4], v[b]);
+                                }
+                            };
+                            int j = ja;
+                            for (; j + B - 1 <= jb; j += B) {       // B read bases per trip: the window of weights rotates through the names
+                                double nw[B];
+#pragma unroll
+                                for (int b = 0; b < B; b++) nw[b] = ld(i0 - 1 - b);
+#pragma unroll
+                                for (int t = 0; t < B; t++) {       // read base j+t: row x+b takes weight index i0 + b - t
+                                    double v[B];
+#pragma unroll
+                                    for (int b = 0; b < B; b++) v[b] = (b - t >= 0) ? w[b - t] : nw[t - b - 1];
+                                    add(rc[j + t], v);
+                                }
+#pragma unroll
+                                for (int b = 0; b < B; b++) w[b] = nw[B - 1 - b];
+                                i0 -= B;
                             }
-                        };
-                        int j = ja;
-                        for (; j + 3 <= jb; j += 4) {       // four read bases per trip: the window of weights rotates through the names
-                            const double n0 = ld(i0 - 1), n1 = ld(i0 - 2), n2 = ld(i0 - 3), n3 = ld(i0 - 4);
-                            add(rc[j], w0, w1, w2, w3);
-                            add(rc[j + 1], n0, w0, w1, w2);
-                            add(rc[j + 2], n1, n0, w0, w1);
-                            add(rc[j + 3], n2, n1, n0, w0);
-                            w3 = n0; w2 = n1; w1 = n2; w0 = n3; i0 -= 4;
-                        }
-                        for (; j <= jb; j++) {
-                            add(rc[j], w0, w1, w2, w3);
-                            i0--;
-                            w3 = w2; w2 = w1; w1 = w0; w0 = ld(i0);
-                        }
-                    }
-                    if (gi < nG) {
+                            for (; j <= jb; j++) {
+                                add(rc[j], w);
+                                i0--;
 #pragma unroll
-                        for (int b = 0; b < 4; b++) {
-                            const int row = x + b;
-                            if (row < Lg) {
+                                for (int b = B - 1; b > 0; b--) w[b] = w[b - 1];
+                                w[0] = ld(i0);
+                            }
+                        }
+                        if (gi < nG) {
 #pragma unroll
-                                for (int k = 0; k < 5; k++) {
-                                    if (split == 1) C[k * Lg + row] = __dadd_rn(C[k * Lg + row], a[b][k]);
-                                    else GP[((size_t)s * 5 + k) * Lg + row] = a[b][k];
+                            for (int b = 0; b < B; b++) {
+                                const int row = x + b;
+                                if (row < Lg) {
+#pragma unroll
+                                    for (int k = 0; k < 5; k++) {
+                                        if (split == 1) C[k * Lg + row] = __dadd_rn(C[k * Lg + row], a[b][k]);
+                                        else GP[((size_t)s * 5 + k) * Lg + row] = a[b][k];
+                                    }
                                 }
                             }
                         }
                     }
-                }
+                };
+                if (rowsPerThread == 4) gather(std::integral_constant<int, 4>()); else gather(std::integral_constant<int, 2>());
                 if (split > 1) {
                     __syncthreads();
                     for (int i = tid; i < 5 * Lg; i += kThreads) {
