@@ -11,9 +11,12 @@
 // the error path, :297; soft clips count as insertions, :339; computeErrorProb does not split CIGARs at 'S', :988).
 #include <cmath>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <algorithm>
+#include <sys/mman.h>
 #include <thread>
+#include <unistd.h>
 
 #include "fb_host.h"
 
@@ -148,14 +151,71 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err) 
     s.errorPos.assign(RL, 1); s.inPos.assign(RL, 1); s.inLengths.assign(RL, 1); s.delPos.assign(RL, 1); s.delLengths.assign(RL, 1); s.readLengths.assign(RL, 0);
     const double inputMean = a.setInputMean == 1 ? (double)a.insertSizeMean : 0.0;   // Figbird.cpp:6973
 
+    const bool timing = getenv("FIGBIRD_MODEL_TIMING") != nullptr;
+    auto tnow = [] { return std::chrono::steady_clock::now(); };
+    auto tprev = tnow();
+    auto lap = [&](const char* what) { if (timing) { auto t = tnow(); fprintf(stderr, "learnModel %-10s %.3f s\n", what, std::chrono::duration<double>(t - tprev).count()); tprev = t; } };
     FILE* mf = fopen(a.myout.c_str(), "r");
     if (!mf) { err = "Can't open map file"; return false; }
-    // whole file in memory once; both passes walk the same lines (the reference reads it twice per worker)
-    std::vector<char> text;
-    { fseek(mf, 0, SEEK_END); long n = ftell(mf); fseek(mf, 0, SEEK_SET); text.resize(n + 1); size_t got = fread(text.data(), 1, n, mf); text[got] = 0; text.resize(got + 1); fclose(mf); }
+    // whole file in memory once; both passes walk the same lines (the reference reads it twice per worker).  The read and
+    // the search for line starts are cut into blocks over the host threads.
+    std::vector<char> textOwned;
     std::vector<char*> lines;
-    for (char* p = text.data(); *p;) { lines.push_back(p); char* e = strchr(p, '\n'); if (!e) break; p = e + 1; }
+    struct Mapping { void* p = nullptr; size_t len = 0; ~Mapping() { if (p) munmap(p, len); } } mapping;
+    char* textBase = nullptr;
+    {
+        fseek(mf, 0, SEEK_END); const long n = ftell(mf); fseek(mf, 0, SEEK_SET);
+        int rt = (int)std::thread::hardware_concurrency();
+        if (const char* e = getenv("FIGBIRD_HOST_THREADS")) rt = atoi(e);
+        rt = std::max(1, std::min(rt, (int)(n / (8 << 20)) + 1));
+        const int fd = fileno(mf);
+        long total = n;
+        // map the page cache instead of copying it; the zero tail of the last page is the terminating NUL
+        // (a file that ends exactly on a page boundary takes the copying path)
+        if (n > 0 && (n % 4096) != 0) {
+            void* mp = mmap(nullptr, (size_t)n, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (mp != MAP_FAILED) { mapping.p = mp; mapping.len = (size_t)n; textBase = (char*)mp; }
+        }
+        std::vector<std::thread> th;
+        if (!textBase) {
+            textOwned.resize((size_t)n + 1);
+            std::vector<long> got(rt, 0);
+            for (int t = 0; t < rt; t++) th.emplace_back([&, t] {
+                const long lo = n * t / rt, hi = n * (t + 1) / rt;
+                long off = lo;
+                while (off < hi) { ssize_t k = pread(fd, textOwned.data() + off, (size_t)(hi - off), off); if (k <= 0) break; off += k; }
+                got[t] = off - lo;
+            });
+            for (auto& t : th) t.join();
+            bool shortRead = false;
+            for (int t = 0; t < rt; t++) if (got[t] != n * (t + 1) / rt - n * t / rt) shortRead = true;
+            if (shortRead) { fclose(mf); err = "Can't read map file"; return false; }
+            textOwned[n] = 0;
+            textBase = textOwned.data();
+        }
+        fclose(mf);
+        std::vector<std::vector<char*>> part(rt);
+        struct { char* d; char* data() const { return d; } } text{textBase};
+        // line starts: position 0 and every position after a '\n' (a trailing '\n' starts no line)
+        th.clear();
+        for (int t = 0; t < rt; t++) th.emplace_back([&, t] {
+            const long lo = total * t / rt, hi = total * (t + 1) / rt;
+            std::vector<char*>& v = part[t];
+            v.reserve((size_t)(hi - lo) / 150 + 16);
+            if (lo == 0 && total > 0) v.push_back(text.data());
+            const char* base = text.data();
+            for (const char* p = (const char*)memchr(base + lo, '\n', (size_t)(hi - lo)); p; p = (const char*)memchr(p + 1, '\n', (size_t)(base + hi - (p + 1)))) {
+                if (p + 1 < base + total) v.push_back(const_cast<char*>(p + 1));
+                if (p + 1 >= base + hi) break;
+            }
+        });
+        for (auto& t : th) t.join();
+        size_t cnt = 0; for (auto& v : part) cnt += v.size();
+        lines.reserve(cnt);
+        for (auto& v : part) lines.insert(lines.end(), v.begin(), v.end());
+    }
     // NB: lines keep their '\n'; tokenisers treat it as a delimiter where the reference does.
+    lap("read+split");
 
     // ---- pass 1: processMapping.  The statistics are integer counts, so the file is cut into blocks that are
     // counted on separate threads and summed -- identical to the sequential result as long as every line carries its
@@ -179,7 +239,8 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err) 
         for (const char* c = f.seq; *c; c++, readLength++) st.baseCounts[baseIndex(*c)]++;
         if (readLength < 1 || readLength > RL) { st.uniqueMappedReads++; return; }
         st.readLengths[readLength - 1]++;
-        std::vector<int> inserts(readLength, 0);
+        static thread_local std::vector<int> inserts;
+        inserts.assign(readLength, 0);
         int index = 0, curIndex = 0;
         walkCigar(f.cigar, "IDMS^\t\n ", [&](char op, int n) {
             if (op == 'M') { index += n; curIndex += n; }
@@ -247,6 +308,7 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err) 
         for (char* ln : lines) pass1Line(s, mdKeep, scratch, ln, ir);
     }
 
+    lap("pass1");
     // ---- computeProbabilites (Figbird.cpp:497-844); only the quantities used downstream are kept
     double baseErrorRates[5];
     for (int i = 0; i < 5; i++) {
@@ -316,7 +378,8 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err) 
         const unsigned long readLength = strlen(read);
         long double ep = (readLength >= 1 && (int)readLength <= RL) ? noErrorProbs[readLength - 1] : 0;
         if (md[5] == '^') return ep;
-        std::vector<int> inserts(readLength, 0);
+        static thread_local std::vector<int> inserts;
+        inserts.assign(readLength, 0);
         int index = 0, curIndex = 0;
         walkCigar(cigar, "IDM^\t\n ", [&](char op, int n) {
             if (op == 'M') { index += n; curIndex += n; }
@@ -344,6 +407,7 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err) 
     };
 
     long gapProbs[1000] = {0};
+    lap("tables");
     if (nThreads <= 1 || irregularAny) {
         std::string pre1 = "*", pre2 = "*";
         long double tempProb = 0, gapProb = 0;
@@ -438,6 +502,7 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err) 
             p1 = r.q1; pn1 = r.n1; p2 = r.q2; pn2 = r.n2;
         }
     }
+    lap("pass2");
     {   // Figbird.cpp:7155-7178
         long gapProbSum = 0; for (int i = 0; i < 1000; i++) gapProbSum += gapProbs[i];
         long gapProbCount = 0; const double value = .8;
