@@ -52,7 +52,13 @@
 
 namespace {
 
-constexpr int kThreads = 384;
+#ifndef FB_THREADS
+#define FB_THREADS 384
+#endif
+#ifndef FB_CTAS
+#define FB_CTAS 2
+#endif
+constexpr int kThreads = FB_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxSmem = 200 * 1024;      // dynamic shared memory we opt in to (227 KB is the sm_100 limit)
 constexpr int kChunkWant = 72 * 1024;     // weights + read-code staging we ask for per CTA when the reads allow it
@@ -112,6 +118,7 @@ __host__ __device__ inline Plan makePlan(int Lg, int F, int modelLen, int maxLen
     p.oG = o; o += al16(p.rows);
     p.oPREV = o; o += al16(Lg);
     p.tableBytes = al16(o);
+    if (p.tableBytes < 12 * kThreads) p.tableBytes = al16(12 * kThreads);     // the prologue's prefix-sum scratch lives here
     o = 0;
     p.oME = o; o += al16(8 * modelLen);
     p.oMT2 = o; o += 16 * modelLen;
@@ -239,7 +246,7 @@ __global__ void __launch_bounds__(128) fb_flank_kernel(const Params prm, int nRe
 }
 
 template <bool TSMEM>
-__global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Params prm, const int* __restrict__ order, const int smemBytes) {
+__global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(const Params prm, const int* __restrict__ order, const int smemBytes) {
     const DevItem it = prm.items[order[blockIdx.x]];
     const DevGap g = prm.gaps[it.gap];
     const DevModel& m = prm.m;
@@ -251,7 +258,6 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
 
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_comp, s_same, s_flags, s_q1, s_next1, s_next2;
-    __shared__ int s_scan[3][kThreads];
     __shared__ unsigned long long s_lane1, s_lane2, s_terms;
 
     unsigned char* const tbase = TSMEM ? smem : (prm.scratch + it.scratch_off);
@@ -304,12 +310,13 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
             sw += n; s1 += (Lg > 0) ? ((n < Lg ? n : Lg) + 31) / 32 : 0; s2 += (n + 63) / 64;
             st += (long long)n * (len - prm.read_jcut[qi] - prm.read_jlo[qi]);
         }
-        s_scan[0][tid] = sw; s_scan[1][tid] = s1; s_scan[2][tid] = s2;
+        int* const s_scan = (int*)UT;          // [3][kThreads] scratch: the row tables are written after this block
+        s_scan[tid] = sw; s_scan[kThreads + tid] = s1; s_scan[2 * kThreads + tid] = s2;
         if (st) atomicAdd(&s_terms, (unsigned long long)st);
         __syncthreads();
-        if (tid < 3) { int acc = 0; for (int i = 0; i < kThreads; i++) { const int v = s_scan[tid][i]; s_scan[tid][i] = acc; acc += v; } }
+        if (tid < 3) { int acc = 0; for (int i = 0; i < kThreads; i++) { const int v = s_scan[tid * kThreads + i]; s_scan[tid * kThreads + i] = acc; acc += v; } }
         __syncthreads();
-        sw = s_scan[0][tid]; s1 = s_scan[1][tid]; s2 = s_scan[2][tid];
+        sw = s_scan[tid]; s1 = s_scan[kThreads + tid]; s2 = s_scan[2 * kThreads + tid];
         for (int q = qb; q < qe; q++) {
             const int n = mt.woff[q];
             mt.woff[q] = sw; mt.u1[q] = s1; mt.u2[q] = s2;
@@ -554,13 +561,11 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
         const int maxCalls = it.max_rounds + ((it.flags & FB_FLAG_EXTRA_PASS) ? 1 : 0);
         bool emDone = it.max_rounds <= 0;
         const long long offLg = (long long)Lg - g.orig_len;
-        // gather geometry: a task = 2 or 4 consecutive gap rows x one part of the reads; parts are combined in order through
-        // a scratch that aliases the row tables (dead between the walk and the M-step), so only when all reads are resident
-        const int rowsPerThread = (Lg >= 3 * kThreads) ? 4 : 2;
+        // gather geometry: a task = 2 or 4 consecutive gap rows x one part of the reads; the parts add their sums to the
+        // count matrix one after the other (fixed order), separated by barriers
+        const int rowsPerThread = (Lg > 64) ? 4 : 2;
         const int nG = (Lg + rowsPerThread - 1) / rowsPerThread, tpp = (nG + 31) & ~31;
-        int split = 1;
-        if (singleChunk && Lg > 0) { split = kThreads / tpp; const int cap = (2 * S) / Lg; split = max(1, min(min(split, cap), 8)); }
-        double* const GP = (double*)UT;
+        const int split = (Lg > 0 && tpp <= kThreads) ? max(1, kThreads / tpp) : 1;     // parts of the reads per row tile
         for (int call = 0; call < maxCalls; call++) {
             const bool extra = emDone;
             const int slot = (it.flags & FB_FLAG_RECORD_ALL) ? call : 0;
@@ -698,8 +703,8 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
                 // per step slides through four registers.
                 auto gather = [&](auto BB) {
                     constexpr int B = BB.value;           // gap rows per thread
-                    for (int idx = tid; idx < tpp * split; idx += kThreads) {
-                        const int s = idx / tpp, gi = idx - s * tpp;
+                    for (int idx = tid; idx < tpp * split || split > 1; idx += kThreads) {
+                        const int s = idx / tpp, gi = idx - s * tpp;      // split > 1: one trip, every thread reaches the barriers below
                         const int x = gi * B;
                         const int xw0 = (gi - lane) * B, xw1 = min(Lg - 1, xw0 + 32 * B - 1);      // rows of this warp
                         double a[B][5];
@@ -707,7 +712,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
                         for (int b = 0; b < B; b++)
 #pragma unroll
                             for (int k = 0; k < 5; k++) a[b][k] = 0.0;
-                        if (xw0 < Lg) for (int ql = s; ql < nq; ql += split) {
+                        if (xw0 < Lg && s < split) for (int ql = s; ql < nq; ql += split) {
                             const RMeta r = RM[ql];
                             if (r.n <= 0) continue;
                             const int len = r.packed & 0xff;
@@ -769,30 +774,23 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? 2 : 1) fb_em_kernel(const Pa
                                 w[0] = ld(i0);
                             }
                         }
-                        if (gi < nG) {
+                        for (int sp = 0; sp < split; sp++) {
+                            if (sp == s && gi < nG) {
 #pragma unroll
-                            for (int b = 0; b < B; b++) {
-                                const int row = x + b;
-                                if (row < Lg) {
+                                for (int b = 0; b < B; b++) {
+                                    const int row = x + b;
+                                    if (row < Lg) {
 #pragma unroll
-                                    for (int k = 0; k < 5; k++) {
-                                        if (split == 1) C[k * Lg + row] = __dadd_rn(C[k * Lg + row], a[b][k]);
-                                        else GP[((size_t)s * 5 + k) * Lg + row] = a[b][k];
+                                        for (int k = 0; k < 5; k++) C[k * Lg + row] = __dadd_rn(C[k * Lg + row], a[b][k]);
                                     }
                                 }
                             }
+                            if (split > 1) __syncthreads();
                         }
+                        if (split > 1) break;
                     }
                 };
                 if (rowsPerThread == 4) gather(std::integral_constant<int, 4>()); else gather(std::integral_constant<int, 2>());
-                if (split > 1) {
-                    __syncthreads();
-                    for (int i = tid; i < 5 * Lg; i += kThreads) {
-                        double acc = C[i];
-                        for (int s = 0; s < split; s++) acc = __dadd_rn(acc, GP[(size_t)s * 5 * Lg + i]);
-                        C[i] = acc;
-                    }
-                }
                 __syncthreads();
             }
             // ================= computeSequence(0,0) =================
