@@ -467,7 +467,18 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                     const unsigned char* rc = RC + ql * mlp;
                     const unsigned char* gs = G + F + r.x1;
                     double p = 1.0;
-                    for (int j = jlo; j < jhi; j++) {
+                    int j = jlo;
+                    for (; j + 4 <= jhi; j += 4) {      // factors first (independent loads), then the ordered product
+                        double v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int c = rc[j + u], f = gs[j + u];
+                            const double2 mk = MT2[rev ? (len - j - u - 1) : (j + u)];
+                            v[u] = (f == c) ? mk.x : __dmul_rn(mk.y, ETP[f * 5 + c]);
+                        }
+                        p = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(p, v[0]), v[1]), v[2]), v[3]);
+                    }
+                    for (; j < jhi; j++) {
                         const int c = rc[j], f = gs[j];
                         const double2 mk = MT2[rev ? (len - j - 1) : j];
                         p = __dmul_rn(p, (f == c) ? mk.x : __dmul_rn(mk.y, ETP[f * 5 + c]));
