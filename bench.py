@@ -11,8 +11,10 @@ fb_fillgaps_main with inputs on the host (files), host<->device copies inside th
              (batch resident in HBM when each kernel starts); explains the roofline.
   e2e.value  reference-equivalent placements / wall time of the timed steps (the headline vs --impl reference).
   roofline   FP64-pipe bound (the path is neither HBM- nor tensor-bound): algorithmic FP64
-             operations (4 per pass-1 base term, 1 per pass-2 base term) / kernel time, against the
-             no-FMA FP64 rate measured on this GPU by fb_microbench_fp64.  HBM GB/s is reported beside it.
+             operations (4 per pass-1 base term, 1 per pass-2 base term) / kernel time (union of the kernel
+             intervals on the device), against the no-FMA FP64 rate measured on this GPU by fb_microbench_fp64.
+             Beside it: the shared-memory view of the pass-1 walk (16 B per executed gap-row term), executed vs
+             algorithmic terms, HBM GB/s, and the counters of the dominant launch from the committed ncu capture.
   cpu_baseline / --impl reference: the reference's own FillGaps + worker (oracle/_ref, as-shipped -O0 worker
              through the g++ shim) on a bounded sample of the same workload, all host cores.
 N>1: weak scaling -- every rank fills its own C2-sized draft (seed + rank), no collective on the path.
@@ -232,11 +234,29 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    roof = {"bound": "fp64 (no-FMA issue rate; the path is not HBM- or tensor-bound, SURVEY.md 8d)", "achieved": ach, "peak": mb["dmul_tinstr_s"], "unit": "TFLOP/s",
-            "frac": ach / mb["dmul_tinstr_s"] if mb["dmul_tinstr_s"] else None, "traffic": None,
+    lane1 = sum(m.get("lane_steps_p1", 0) for m in metrics); lane2 = sum(m.get("lane_steps_p2", 0) for m in metrics)
+    ncu = {}
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
+    except Exception:
+        pass
+    dom = ncu.get("unmapped", {})      # the unmapped-mode launches carry ~3/4 of the kernel time (profiles/README.md)
+    smem_peak = 128.0 * torch.cuda.get_device_properties(local).multi_processor_count * (sampler.summary()["sm_mhz"] or 1965.0) * 1e6 / 1e9
+    roof = {"bound": "fp64 issue without FMA (4 separately rounded ops per pass-1 term as the reference computes them); co-limited by the "
+                     "shared-memory crossbar: one 16-byte table entry per gap-row term (DESIGN.md 3).  Not HBM- or tensor-bound (SURVEY.md 8d)",
+            "achieved": ach, "peak": mb["dmul_tinstr_s"], "unit": "TFLOP/s",
+            "frac": ach / mb["dmul_tinstr_s"] if mb["dmul_tinstr_s"] else None,
+            "traffic": dom.get("dram_bytes_per_launch"),
+            "traffic_note": "dram__bytes_read+write of the dominant fb_em_kernel launch (ncu --set full, profiles/ncu_summary.json: %s, grid %s, %.1f ms); algorithmic HBM bytes of that launch ~= inputs once + result arena"
+                            % (dom.get("file"), dom.get("grid"), dom.get("duration_ms", 0.0)) if dom else None,
             "peak_source": "fb_microbench_fp64 on this GPU (DMUL chains, 1 flop/instr); DFMA rate %.1f TFLOP/s" % mb["dfma_tflops"],
-            "algorithmic": "4 FP64 ops per pass-1 base term, 1 per pass-2 base term; %.3e base terms per step" % (terms / max(a.steps, 1)),
+            "algorithmic": "4 FP64 ops per pass-1 base term, 1 per pass-2 base term (SURVEY.md 8d); %.3e base terms per step" % (terms / max(a.steps, 1)),
             "kernel_ms_per_launch": dev_ms / max(launches, 1),
+            "executed_vs_algorithmic": {"pass1_lane_steps": lane1, "pass2_lane_steps": lane2, "algorithmic_terms_pass1": t1, "algorithmic_terms_pass2": t2,
+                                        "note": "flank terms come from the per-gap cache and pass 2 is pruned, so the kernel walks fewer terms than the reference evaluates"},
+            "smem": {"achieved_gbs": 16.0 * lane1 / (dev_ms * 1e-3) / 1e9, "peak_gbs": smem_peak, "frac": 16.0 * lane1 / (dev_ms * 1e-3) / 1e9 / smem_peak,
+                     "note": "pass-1 walk only: 16 B (LDS.128 of {P, E-P}) per executed gap-row lane step / kernel time, against 128 B/clk/SM x SMs x SM clock"},
+            "ncu": {k: dom.get(k) for k in ("issue_active_pct", "smem_wavefronts_pct", "fp64_pipe_pct", "alu_pipe_pct", "lsu_pipe_pct", "warps_active_pct", "stall_barrier")} if dom else None,
             "hbm": {"achieved_gbs": (h2d + d2h) / (dev_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                     "note": "algorithmic HBM bytes ~= result arena + inputs; tables live in shared memory"}}
     line = {"metric": metric, "value": dev_p1_all / (devms_max * 1e-3), "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -246,8 +266,6 @@ def main():
                     "note": "through fb_fillgaps_main: files -> model -> per-gap control on host threads -> engine; reference-equivalent pass-1 placements / wall",
                     "gaps_per_s": (len(open(os.path.join(case, "partial", "Temp", "gapInfo.txt")).readlines()) * world * a.steps) / dt_max,
                     "host_seconds_per_step": {k: sum(m[k] for m in metrics) / a.steps for k in ("t_load", "t_model", "t_prepare", "t_fill", "t_write")}},
-            "executed": {"pass1_gap_row_lane_steps": sum(m.get("lane_steps_p1", 0) for m in metrics), "pass2_lane_steps": sum(m.get("lane_steps_p2", 0) for m in metrics),
-                         "algorithmic_base_terms": terms, "note": "rank 0, all timed steps: terms the kernel walked (flank terms cached per gap, pass 2 pruned) vs. terms the reference evaluates"},
             "gpu_launches": int(launches_all), "device_placements_p1": dev_p1_all, "device_placements_p2": dev_p2_all, "roofline": roof}
     if world == 1 and not a.no_cpu_baseline and fc.have_reference():
         sample = prepare_case(os.path.join(base, "sample"), SAMPLE, 1102)

@@ -9,5 +9,5 @@ python - <<PY
 import json
 d=json.load(open("gpurun_out/bench_$tag.json"))
 print("value %.3e e2e %.3e ms/step %.0f launches %d kernel_ms/launch %.2f frac %.4f" % (d["value"], d["e2e"]["value"], d["ms_per_step"], d["gpu_launches"], d["roofline"]["kernel_ms_per_launch"], d["roofline"]["frac"]))
-print(d["e2e"]["host_seconds_per_step"]); print(d.get("executed"))
+print(d["e2e"]["host_seconds_per_step"]); print({k: d["roofline"].get(k) for k in ("smem", "traffic")})
 PY
