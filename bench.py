@@ -42,7 +42,8 @@ SAMPLE = ({"genome": 294400, "scaffolds": 2, "gaps": 32, "gapmin": 10, "gapmax":
 
 
 def rank_info():
-    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    from figbird_b200.ranks import rank_info as ri
+    return ri()
 
 
 def prepare_case(path, spec, seed):
@@ -206,14 +207,10 @@ def main():
     terms = sum(m["dev_base_terms"] for m in metrics)
     launches = sum(m["kernel_launches"] for m in metrics)
     h2d = sum(m["h2d_bytes"] for m in metrics); d2h = sum(m["d2h_bytes"] for m in metrics)
-    vals = torch.tensor([dt, dev_ms, dev_p1, ref_p1, launches, terms, dev_p2], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        dt_max, devms_max = mx[0].item(), mx[1].item()
-        dev_p1_all, ref_p1_all, launches_all, terms_all, dev_p2_all = sm[2].item(), sm[3].item(), sm[4].item(), sm[5].item(), sm[6].item()
-    else:
-        dt_max, devms_max, dev_p1_all, ref_p1_all, launches_all, terms_all, dev_p2_all = dt, dev_ms, dev_p1, ref_p1, launches, terms, dev_p2
+    from figbird_b200.ranks import reduce_counters
+    mx, sm = reduce_counters({"dt": dt, "dev_ms": dev_ms, "dev_p1": dev_p1, "ref_p1": ref_p1, "launches": launches, "terms": terms, "dev_p2": dev_p2}, dist, "cuda")
+    dt_max, devms_max = mx["dt"], mx["dev_ms"]
+    dev_p1_all, ref_p1_all, launches_all, terms_all, dev_p2_all = sm["dev_p1"], sm["ref_p1"], sm["launches"], sm["terms"], sm["dev_p2"]
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

@@ -7,7 +7,7 @@ synthetic SAM) and what the reference FillGaps + Figbird worker produced from th
   expected/<mode>/model.txt        learned tables dumped by the instrumented worker (oracle/dump_patch.awk)
   expected/<mode>/counts.txt       a sample of the worker's countsGap dumps: (gap, Lg, round) -> gap rows %.17g
 
-Run:  python tests/make_golden.py        (a few minutes; commits nothing by itself)
+Run:  python tests/make_golden.py [names]   (minutes per fixture; commits nothing by itself)
 """
 import os
 import shutil
@@ -21,6 +21,10 @@ import fbcase as fc  # noqa: E402
 CASES = {
     "g1": dict(gen={"genome": 24000, "gaplist": "12,45,95,170", "seed": 21, "cov": 30}, readlen=100, insert=200),
     "g2": dict(gen={"genome": 44000, "gaplist": "8,30,250,460,25", "seed": 22, "cov": 30, "negfrac": 0.3, "readN": 30}, readlen=100, insert=200),
+    # BASELINE configs[3] parameters (2x150 bp at 500 bp insert) at fixture size
+    "g3": dict(gen={"genome": 40000, "gaplist": "15,90,260", "seed": 23, "cov": 30, "sd": 50}, readlen=150, insert=500),
+    # BASELINE configs[2]'s second library (3500 bp insert, maxDistance 4025): every offset of the window is admissible
+    "g4": dict(gen={"genome": 50000, "gaplist": "20,110", "seed": 24, "cov": 20, "sd": 350}, readlen=100, insert=3500),
 }
 
 
@@ -52,7 +56,10 @@ def main():
     assert fc.have_reference(), "oracle/_ref missing: /root/reference is needed to regenerate goldens"
     outdir = os.path.join(HERE, "golden")
     os.makedirs(outdir, exist_ok=True)
+    only = sys.argv[1:]
     for name, spec in CASES.items():
+        if only and name not in only:
+            continue
         case = os.path.join("/tmp", "fb_golden_" + name)
         shutil.rmtree(case, ignore_errors=True)
         fc.make_case(case, spec["gen"], readlen=spec["readlen"], insert=spec["insert"])
