@@ -176,6 +176,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     os.environ["FIGBIRD_GPUS"] = str(local)
+    if world > 1 and "FIGBIRD_HOST_THREADS" not in os.environ:      # ranks of one box share its host cores
+        os.environ["FIGBIRD_HOST_THREADS"] = str(max(2, cores // world))
     case = prepare_case(os.path.join(base, "%s_rank%d" % (a.workload, rank)), WORKLOADS[a.workload], 102 + rank)
     work = os.path.join(base, "work_rank%d" % rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")

@@ -58,6 +58,12 @@ namespace {
 #ifndef FB_CTAS
 #define FB_CTAS 2
 #endif
+#ifndef FB_FUSE1
+#define FB_FUSE1 0      // 1: the warp that completes a read's last pass-1 unit finishes the read inside the unit loop
+#endif
+#ifndef FB_FUSE2
+#define FB_FUSE2 0      // same for pass 2
+#endif
 constexpr int kThreads = FB_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxSmem = 200 * 1024;      // dynamic shared memory we opt in to (227 KB is the sm_100 limit)
@@ -127,7 +133,7 @@ __host__ __device__ inline Plan makePlan(int Lg, int F, int modelLen, int maxLen
     int n = (mode == FB_MODE_UNMAPPED) ? (maxLen + Lg - 1) : (maxLen - 1);
     if (mode == FB_MODE_UNMAPPED && bandMax < n) n = bandMax;     // unmapped reads always pass through the insert-size filter
     p.nMax = n > 1 ? n : 1;
-    p.perRead = 8 * p.nMax + p.maxLenPad + 40;       // weights + codes + record + threshold
+    p.perRead = 8 * p.nMax + p.maxLenPad + 56;       // weights + codes + record + threshold + unit counters
     return p;
 }
 
@@ -257,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
     const int S = pl.S, rows = pl.rows, mlp = pl.maxLenPad;
 
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ int s_comp, s_same, s_flags, s_q1, s_next1, s_next2;
+    __shared__ int s_same[2], s_gchg, s_flags, s_q1, s_next1, s_next2;
     __shared__ unsigned long long s_lane1, s_lane2, s_terms;
 
     unsigned char* const tbase = TSMEM ? smem : (prm.scratch + it.scratch_off);
@@ -285,7 +291,9 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
     const unsigned char* lf = prm.flank + g.flank_begin;
     const unsigned char* rf = lf + F;
 
-    if (tid == 0) { s_comp = 0; s_flags = 0; s_lane1 = 0; s_lane2 = 0; s_terms = 0; }
+    if (tid == 0) { s_same[0] = 1; s_same[1] = 1; s_gchg = 0; s_next1 = 0; s_next2 = 0; s_flags = 0; s_lane1 = 0; s_lane2 = 0; s_terms = 0; }
+    int comp = 0;          // comp_count (Figbird.cpp:3919-3927), kept identically by every thread
+    bool gChanged = true;  // the gap string differs from the one the cached pass-2 thresholds were computed on
     // ---- model tables, flank part of the gap string
     for (int k = tid; k < m.max_read_len; k += kThreads) { const double e = m.e[k]; ME[k] = e; MT2[k] = make_double2(m.match[k], e); }
     if (tid < 25) ETP[tid] = m.etp[tid];
@@ -330,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
         sumTerms = (long long)s_terms;
     }
     const int totalW = (int)sumN;
-    const bool singleChunk = (8LL * totalW + (long long)R * (mlp + 40) + 64) <= (long long)chunkBytes;
+    const bool singleChunk = (8LL * totalW + (long long)R * (mlp + 56) + 96) <= (long long)chunkBytes;
     int prevValid = 0;   // previous hard consensus present (uniform)
 
     auto storeRow = [&](int x, const double p[4], const double e[5]) {     // gap row x and its cyclic copies
@@ -346,7 +354,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
             const double* cin = (const double*)(prm.in_arena + it.counts_in_off);
             for (int i = tid; i < 5 * Lg; i += kThreads) { int x = i / 5, k = i % 5; C[k * Lg + x] = cin[i]; }
             if (it.string_in_off >= 0) { const unsigned char* sin = prm.in_arena + it.string_in_off; for (int x = tid; x < Lg; x += kThreads) PREV[x] = sin[x]; prevValid = 1; }
-            if (tid == 0) s_comp = it.comp_in;
+            comp = it.comp_in;
         } else {
             // gap rows from the partial pile-ups (update_partial_prob, Figbird.cpp:2039-2081)
             const int* plp = prm.pile_l + 4 * (size_t)g.pile_begin; const int* prp = prm.pile_r + 4 * (size_t)g.pile_begin;
@@ -376,11 +384,13 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
     struct RMeta { int xlo, wrel, n, packed, rel, u1, u2, x1; };     // packed = len | jlo<<8 | jhi<<16 | flags<<24; wrel/u1/u2 relative to the chunk
     RMeta* const RM = (RMeta*)chunkBase;
     int nqCur = 0;                       // reads in the resident chunk (uniform)
-    double* THR = nullptr; unsigned char* RC = nullptr; double* W = nullptr;
+    double* THR = nullptr; int* CNT = nullptr; int* X1P = nullptr; unsigned char* RC = nullptr; double* W = nullptr;
     auto carveChunk = [&](int nq) {
         nqCur = nq;
-        THR = (double*)(chunkBase + 32 * (size_t)(nq + 1));
-        RC = (unsigned char*)THR + al16(8 * nq);
+        THR = (double*)(chunkBase + 32 * (size_t)(nq + 1));      // exact pass-2 product at X1P (pruning threshold)
+        CNT = (int*)((unsigned char*)THR + al16(8 * nq));        // [2][nq] finished pass-1 / pass-2 units of a read
+        X1P = CNT + 2 * nq;                                      // offset THR was computed at
+        RC = (unsigned char*)CNT + al16(12 * nq);
         W = (double*)(RC + (size_t)nq * mlp);
     };
     auto stageReads = [&](int q0, int q1) {   // read records and codes of the chunk
@@ -397,6 +407,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                 r.packed = len | (prm.read_jlo[qi] << 8) | ((len - prm.read_jcut[qi]) << 16) | (prm.read_flags[qi] << 24);
             } else { r.xlo = 0; r.n = 0; r.rel = 0; r.x1 = INT_MIN; r.packed = 0; }
             RM[ql] = r;
+            if (ql < nq) { CNT[ql] = 0; CNT[nq + ql] = 0; X1P[ql] = INT_MIN; THR[ql] = 0.0; }
         }
         const int n = nq * mlp;
         for (int i = tid; i < n; i += kThreads) {
@@ -410,8 +421,8 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
         if (singleChunk) return R;
         __syncthreads();
         if (tid == 0) {
-            int q = q0; long long bytes = 64;
-            while (q < R) { const long long nb = 8LL * (mt.woff[q + 1] - mt.woff[q]) + mlp + 40; if (q > q0 && bytes + nb > chunkBytes) break; bytes += nb; q++; }
+            int q = q0; long long bytes = 96;
+            while (q < R) { const long long nb = 8LL * (mt.woff[q + 1] - mt.woff[q]) + mlp + 56; if (q > q0 && bytes + nb > chunkBytes) break; bytes += nb; q++; }
             s_q1 = q;
         }
         __syncthreads();
@@ -429,8 +440,8 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
     __syncthreads();
 
     // M-step over the gap rows (flank rows never change): computeProbsGap(0) + computeErrorProbsGap
-    auto mstep = [&]() {
-        for (int x = tid; x < Lg; x += kThreads) {
+    auto mstepRow = [&](int x) {
+        {
             double c[5];
 #pragma unroll
             for (int k = 0; k < 5; k++) c[k] = C[k * Lg + x];
@@ -445,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
             storeRow(x, p, e);
         }
     };
-    if (it.kind == FB_ITEM_EM && (it.flags & FB_FLAG_RESUME)) { mstep(); __syncthreads(); }
+    if (it.kind == FB_ITEM_EM && (it.flags & FB_FLAG_RESUME)) { for (int x = tid; x < Lg; x += kThreads) mstepRow(x); __syncthreads(); }
 
     // ---- pass 2: products of exact table entries against the gap string, first maximum, accept, unit votes
     auto pass2 = [&](int slot, bool vote) {
@@ -458,8 +469,11 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
             // (FbItemOut: p2max / pos2 of rejected reads are unspecified below the threshold); HARD items stay exact.
             const double floorP = (vote && m.prunable && m.accept_min_p < 1e300) ? m.accept_min_p : 0.0;
             if (tid == 0) s_next2 = 0;
+            // the threshold of the previous round stays exact when neither the gap string nor the seed offset changed
+            const bool reuseThr = singleChunk && !gChanged;
             for (int ql = tid; ql < nq; ql += kThreads) {
                 const RMeta r = RM[ql];
+                if (reuseThr && X1P[ql] == r.x1) continue;
                 double thr = 0.0;
                 if (r.x1 != INT_MIN && m.prunable) {
                     const int len = r.packed & 0xff, jlo = (r.packed >> 8) & 0xff, jhi = (r.packed >> 16) & 0xff;
@@ -485,9 +499,36 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                     }
                     thr = p;
                 }
-                THR[ql] = thr;
+                THR[ql] = thr; X1P[ql] = r.x1;
             }
             __syncthreads();
+            // first maximum over ascending offsets (strict >), accept test, unit votes (Figbird.cpp:3787-3912): by one warp
+            auto finishRead2 = [&](int ql) {
+                const RMeta r = RM[ql];
+                const int q = q0 + ql, len = r.packed & 0xff;
+                const int xlo = r.xlo, n = r.n;
+                const double* Wq = W + r.wrel;
+                double best = -1.0; int bestI = 0x7fffffff;
+                for (int i = lane; i < n; i += 32) { double v = Wq[i]; if (v > best) { best = v; bestI = i; } }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    double ov = __shfl_xor_sync(0xffffffffu, best, o); int oi = __shfl_xor_sync(0xffffffffu, bestI, o);
+                    if (ov > best || (ov == best && oi < bestI)) { best = ov; bestI = oi; }
+                }
+                const int bestx = (best >= 0) ? xlo + bestI : 0;
+                if (lane == 0) { oP2[(size_t)slot * R + q] = best; oPos[(size_t)slot * R + q] = bestx; }
+                if (vote && unm && best >= m.accept_min_p) {
+                    const unsigned char* rc = RC + ql * mlp;
+                    for (int j = lane; j < len; j += 32) { int x = bestx + j; if (x >= 0 && x < Lg) atomicAdd(&NC[rc[j] * Lg + x], 1); }
+                    if (lane == 0 && g.orig_len <= 30) {
+                        int fo = 0; const int p0 = bestx, val = p0 + len - Lg;
+                        if (p0 < 0 && val > 0 && -p0 > 3 && val > 3) fo |= 4;
+                        if (p0 < 0 && p0 + len > 0 && -p0 > 3) fo |= 1;
+                        if (p0 > 0 && p0 < Lg && val > 0 && val > 3) fo |= 2;
+                        if (fo) atomicOr(&s_flags, fo);
+                    }
+                }
+            };
             const int units = RM[nq].u2;
             for (;;) {
                 int u = 0;
@@ -531,35 +572,21 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                 }
                 if (ina) W[r.wrel + ia] = acta ? pa : thrX;
                 if (inb) W[r.wrel + ib] = actb ? pb : thrX;
+#if FB_FUSE2
+                // the warp that completes the last unit of a read finishes the read (its products are all in W by then)
+                __threadfence_block();
+                int done = 0;
+                if (lane == 0) done = atomicAdd(&CNT[nq + ql], 1) + 1;
+                done = __shfl_sync(0xffffffffu, done, 0);
+                if (done == RM[ql + 1].u2 - r.u2) { __threadfence_block(); if (lane == 0) CNT[nq + ql] = 0; finishRead2(ql); }
+#endif
             }
+#if FB_FUSE2
+            for (int ql = warp; ql < nq; ql += kWarps) if (RM[ql + 1].u2 == RM[ql].u2) finishRead2(ql);      // reads without offsets
+#else
             __syncthreads();
-            // first maximum over ascending offsets (strict >), accept test, unit votes (Figbird.cpp:3787-3912)
-            for (int ql = warp; ql < nq; ql += kWarps) {
-                const RMeta r = RM[ql];
-                const int q = q0 + ql, len = r.packed & 0xff;
-                const int xlo = r.xlo, n = r.n;
-                const double* Wq = W + r.wrel;
-                double best = -1.0; int bestI = 0x7fffffff;
-                for (int i = lane; i < n; i += 32) { double v = Wq[i]; if (v > best) { best = v; bestI = i; } }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    double ov = __shfl_xor_sync(0xffffffffu, best, o); int oi = __shfl_xor_sync(0xffffffffu, bestI, o);
-                    if (ov > best || (ov == best && oi < bestI)) { best = ov; bestI = oi; }
-                }
-                const int bestx = (best >= 0) ? xlo + bestI : 0;
-                if (lane == 0) { oP2[(size_t)slot * R + q] = best; oPos[(size_t)slot * R + q] = bestx; }
-                if (vote && unm && best >= m.accept_min_p) {
-                    const unsigned char* rc = RC + ql * mlp;
-                    for (int j = lane; j < len; j += 32) { int x = bestx + j; if (x >= 0 && x < Lg) atomicAdd(&NC[rc[j] * Lg + x], 1); }
-                    if (lane == 0 && g.orig_len <= 30) {
-                        int fo = 0; const int p0 = bestx, val = p0 + len - Lg;
-                        if (p0 < 0 && val > 0 && -p0 > 3 && val > 3) fo |= 4;
-                        if (p0 < 0 && p0 + len > 0 && -p0 > 3) fo |= 1;
-                        if (p0 > 0 && p0 < Lg && val > 0 && val > 3) fo |= 2;
-                        if (fo) atomicOr(&s_flags, fo);
-                    }
-                }
-            }
+            for (int ql = warp; ql < nq; ql += kWarps) finishRead2(ql);
+#endif
             __syncthreads();
         }
     };
@@ -580,14 +607,51 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
         for (int call = 0; call < maxCalls; call++) {
             const bool extra = emDone;
             const int slot = (it.flags & FB_FLAG_RECORD_ALL) ? call : 0;
+            // (no barrier of its own: the walk does not touch C / NC, and a barrier separates it from the gather)
             for (int i = tid; i < 5 * Lg; i += kThreads) { C[i] = 0.0; NC[i] = 0; }
-            if (tid == 0) s_next1 = 0;
-            __syncthreads();
+            if (tid == 0) { s_same[call & 1] = 1; s_gchg = 0; }      // (the other parity may still be read by slow warps of the previous round)
             // ================= pass 1 (Figbird.cpp:3082-3263, 3530-3689) =================
             for (int q0 = 0, q1; q0 < R; q0 = q1) {
                 q1 = chunkEnd(q0);
                 if (!singleChunk) { stageReads(q0, q1); __syncthreads(); }
                 const int nq = q1 - q0;
+                // ---- finish a read: insert pdf x left-flank product x gap product x right-flank product for every placement,
+                //      per-read maximum (value and offset), soft weight in place.  Run by one warp.
+                auto finishRead1 = [&](int ql) {
+                    const RMeta r = RM[ql];
+                    const int q = q0 + ql, qi = g.read_begin + q;
+                    const int len = r.packed & 0xff, jlo = (r.packed >> 8) & 0xff, jhi = (r.packed >> 16) & 0xff, fl = (r.packed >> 24) & 0xff;
+                    const int xlo = r.xlo, n = r.n, rel = r.rel;
+                    double* const Wq = W + r.wrel;
+                    const double* LF = prm.lfrf + 2 * prm.read_off[qi];
+                    const double* RF = LF + len;
+                    double best = 0.0; int bestI = 0x7fffffff;
+                    for (int i = lane; i < n; i += 32) {
+                        const int x0 = xlo + i;
+                        double p = 1.0;
+                        if (unm) {
+                            const long long t = (fl & FB_READ_LEFT) ? ((long long)x0 - rel + len) : ((long long)rel + offLg + len - x0);
+                            p = m.pdf[min(max((int)t, 0), m.n_insert - 1)];
+                        }
+                        if (x0 < 0) p = __dmul_rn(p, LF[-x0]);
+                        if (min(jhi, Lg - x0) > max(jlo, -x0)) p = __dmul_rn(p, Wq[i]);
+                        const int b = x0 + len - Lg;
+                        if (b > 0) p = __dmul_rn(p, RF[b]);
+                        double w = 0.0;
+                        if (p > 0.0) w = placementWeight(p, unm); else p = 0.0;
+                        Wq[i] = w;
+                        if (p > best) { best = p; bestI = i; }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        double ov = __shfl_xor_sync(0xffffffffu, best, o); int oi = __shfl_xor_sync(0xffffffffu, bestI, o);
+                        if (ov > best || (ov == best && oi < bestI)) { best = ov; bestI = oi; }
+                    }
+                    if (lane == 0) {
+                        const int x1 = (best > 0.0) ? xlo + bestI : INT_MIN;
+                        oP1[(size_t)slot * R + q] = (best > 0.0) ? best : -1.0; RM[ql].x1 = x1; mt.x1[q] = x1;
+                    }
+                };
                 // ---- gap-row products of every admissible placement: cyclic diagonal walk
                 const int units = (Lg > 0) ? RM[nq].u1 : 0;
                 for (;;) {
@@ -608,7 +672,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                     int js, je;
                     if (full) { js = jlo; je = jhi; }
                     else { const int xf = xlo + uu * 32, xl = min(xf + 31, xlo + n - 1); js = max(jlo, -xl); je = min(jhi, Lg - xf); }
-                    if (je <= js) continue;
+                    if (je > js) {      // (a unit whose lanes own no gap row still counts towards its read below)
                     const int xi = active ? (full ? idx : xlo + idx) : (full ? 0 : xlo);
                     int xm = xi % Lg; if (xm < 0) xm += Lg;
                     const int m0 = (xm + js) / Lg;
@@ -667,47 +731,24 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                         if (active && (unsigned)(x0cur - xlo) < (unsigned)n) Wq[x0cur - xlo] = acc;
                     }
                     if (lane == 0) atomicAdd(&s_lane1, (unsigned long long)(je - js) * 32ull);
+                    }
+#if FB_FUSE1
+                    // the warp that completes the last unit of a read finishes the read (all its products are in W by then)
+                    __threadfence_block();
+                    int done = 0;
+                    if (lane == 0) done = atomicAdd(&CNT[ql], 1) + 1;
+                    done = __shfl_sync(0xffffffffu, done, 0);
+                    if (done == RM[ql + 1].u1 - r.u1) { __threadfence_block(); if (lane == 0) CNT[ql] = 0; finishRead1(ql); }
+#endif
                 }
+#if FB_FUSE1
+                for (int ql = warp; ql < nq; ql += kWarps) if (Lg <= 0 || RM[ql + 1].u1 == RM[ql].u1) finishRead1(ql);      // reads without gap-row units
+#else
+                __syncthreads();
+                for (int ql = warp; ql < nq; ql += kWarps) finishRead1(ql);
+#endif
                 __syncthreads();
                 if (tid == 0) s_next1 = 0;      // every warp has left the unit loop; the next one starts after further barriers
-                // ---- finish every placement: insert pdf x left-flank product x gap product x right-flank product,
-                //      per-read maximum (value and offset), soft weight in place
-                for (int ql = warp; ql < nq; ql += kWarps) {
-                    const RMeta r = RM[ql];
-                    const int q = q0 + ql, qi = g.read_begin + q;
-                    const int len = r.packed & 0xff, jlo = (r.packed >> 8) & 0xff, jhi = (r.packed >> 16) & 0xff, fl = (r.packed >> 24) & 0xff;
-                    const int xlo = r.xlo, n = r.n, rel = r.rel;
-                    double* const Wq = W + r.wrel;
-                    const double* LF = prm.lfrf + 2 * prm.read_off[qi];
-                    const double* RF = LF + len;
-                    double best = 0.0; int bestI = 0x7fffffff;
-                    for (int i = lane; i < n; i += 32) {
-                        const int x0 = xlo + i;
-                        double p = 1.0;
-                        if (unm) {
-                            const long long t = (fl & FB_READ_LEFT) ? ((long long)x0 - rel + len) : ((long long)rel + offLg + len - x0);
-                            p = m.pdf[min(max((int)t, 0), m.n_insert - 1)];
-                        }
-                        if (x0 < 0) p = __dmul_rn(p, LF[-x0]);
-                        if (min(jhi, Lg - x0) > max(jlo, -x0)) p = __dmul_rn(p, Wq[i]);
-                        const int b = x0 + len - Lg;
-                        if (b > 0) p = __dmul_rn(p, RF[b]);
-                        double w = 0.0;
-                        if (p > 0.0) w = placementWeight(p, unm); else p = 0.0;
-                        Wq[i] = w;
-                        if (p > best) { best = p; bestI = i; }
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        double ov = __shfl_xor_sync(0xffffffffu, best, o); int oi = __shfl_xor_sync(0xffffffffu, bestI, o);
-                        if (ov > best || (ov == best && oi < bestI)) { best = ov; bestI = oi; }
-                    }
-                    if (lane == 0) {
-                        const int x1 = (best > 0.0) ? xlo + bestI : INT_MIN;
-                        oP1[(size_t)slot * R + q] = (best > 0.0) ? best : -1.0; RM[ql].x1 = x1; mt.x1[q] = x1;
-                    }
-                }
-                __syncthreads();
                 // ---- gather the weights of this chunk into the gap rows in a fixed order (deterministic, no FP atomics).
                 // A thread owns 4 consecutive rows x..x+3 and one part of the reads; all lanes of a warp walk the same read
                 // base j (uniform code -> uniform branch), row x+b takes the weight of placement x+b-j: one new weight
@@ -810,42 +851,43 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
 #pragma unroll
                 for (int k = 0; k < 5; k++) { double v = C[k * Lg + x]; if (v > mx) { mx = v; mi = k; } }
                 unsigned char c = (mi >= 0 && mi < 4) ? (unsigned char)mi : 4;
+                if (call == 0 || G[F + x] != c) s_gchg = 1;      // benign race: all writers store 1
                 G[F + x] = c; oSoft[x] = c;
             }
             __syncthreads();
+            gChanged = (call == 0) || (s_gchg != 0);
             // ================= pass 2 =================
             pass2(slot, true);
-            // ================= computeSequence(1,1) + comp_count (Figbird.cpp:3916-3927) =================
-            if (unm) {
-                if (tid == 0) s_same = 1;
-                __syncthreads();
+            // ================= computeSequence(1,1) + comp_count (Figbird.cpp:3916-3927), M-step =================
+            // one sweep over the gap rows: hard consensus / coverage from the votes, and (unless this was the extra pass) the
+            // M-step of the row; one barrier, after which every thread updates its copy of comp_count from the shared flag
+            {
                 int same = prevValid;
                 for (int x = tid; x < Lg; x += kThreads) {
-                    int mx = 0, mi = -1;
+                    if (unm) {
+                        int mx = 0, mi = -1;
 #pragma unroll
-                    for (int k = 0; k < 5; k++) { int v = TSMEM ? NC[k * Lg + x] : __ldcg(&NC[k * Lg + x]); if (v > mx) { mx = v; mi = k; } }
-                    unsigned char h = (mx > 0 && mi >= 0 && mi < 4) ? (unsigned char)mi : 4;
-                    oHard[x] = h; oCov[x] = mx;
-                    if (!prevValid || PREV[x] != h) same = 0;
-                    PREV[x] = h;
+                        for (int k = 0; k < 5; k++) { int v = TSMEM ? NC[k * Lg + x] : __ldcg(&NC[k * Lg + x]); if (v > mx) { mx = v; mi = k; } }
+                        unsigned char h = (mx > 0 && mi >= 0 && mi < 4) ? (unsigned char)mi : 4;
+                        oHard[x] = h; oCov[x] = mx;
+                        if (!prevValid || PREV[x] != h) same = 0;
+                        PREV[x] = h;
+                    } else { oHard[x] = 4; oCov[x] = 0; }
+                    if (!extra) mstepRow(x);
                 }
-                if (!same && Lg > 0) s_same = 0;   // benign race: all writers store 0
-                __syncthreads();
-                // an empty previous string equals the new one only when Lg == 0
-                const int equal = (Lg == 0) ? 1 : (prevValid && s_same);
-                if (tid == 0) s_comp = equal ? s_comp + 1 : 0;
-                prevValid = 1;
-            } else {
-                for (int x = tid; x < Lg; x += kThreads) { oHard[x] = 4; oCov[x] = 0; }
+                if (unm && !same && Lg > 0) s_same[call & 1] = 0;   // benign race: all writers store 0
             }
             calls++;
             __syncthreads();
+            if (unm) {
+                // an empty previous string equals the new one only when Lg == 0
+                const int equal = (Lg == 0) ? 1 : (prevValid && s_same[call & 1]);
+                comp = equal ? comp + 1 : 0;
+                prevValid = 1;
+            }
             if (extra) break;
-            // ================= M-step =================
-            mstep();
-            if (unm && !(it.flags & FB_FLAG_NO_COMP_STOP) && s_comp >= 5) emDone = true;
+            if (unm && !(it.flags & FB_FLAG_NO_COMP_STOP) && comp >= 5) emDone = true;
             if (call + 1 >= it.max_rounds) emDone = true;
-            __syncthreads();
             if (emDone && !(it.flags & FB_FLAG_EXTRA_PASS)) break;
         }
         if (it.off_counts >= 0) {
@@ -857,7 +899,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
     if (tid == 0) {
         FbItemOut* H = (FbItemOut*)out;
         const long long p1calls = (it.kind == FB_ITEM_HARD) ? 0 : calls;
-        H->calls = calls; H->comp_count = s_comp; H->flags = s_flags; H->placements = sumN * p1calls;
+        H->calls = calls; H->comp_count = comp; H->flags = s_flags; H->placements = sumN * p1calls;
         atomicAdd(&prm.counters[0], (unsigned long long)(sumN * p1calls)); atomicAdd(&prm.counters[1], (unsigned long long)(sumN * calls));
         atomicAdd(&prm.counters[2], (unsigned long long)(sumTerms * (p1calls + calls)));
         atomicAdd(&prm.counters[3], s_lane1); atomicAdd(&prm.counters[4], s_lane2);

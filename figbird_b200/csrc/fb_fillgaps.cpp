@@ -196,7 +196,9 @@ int fillgapsMain(int argc, const char* const* argv) {
     const int nG = (int)gaps.size();
     std::vector<std::unique_ptr<GapFill>> fills(nG);
     const int ioThreads = std::max(1, std::min(a.numThreads > 0 ? a.numThreads : 1, 64));
-    parallelFor(nG, std::max(ioThreads, (int)std::thread::hardware_concurrency()), [&](int g) {
+    int hostThreads = std::max(ioThreads, (int)std::thread::hardware_concurrency());
+    if (const char* e = getenv("FIGBIRD_HOST_THREADS")) hostThreads = std::max(1, atoi(e));     // several ranks on one host share its cores
+    parallelFor(nG, hostThreads, [&](int g) {
         GapInput in; in.rec = gaps[g];
         loadPartial(a.gapsDir + "partial_gaps_" + std::to_string(g) + ".sam", in.partial, in.partialExists);
         if (a.unmapped == 1) loadUnmapped(a.gapsDir + "gaps_" + std::to_string(g) + ".sam", a.readLength, in.unm, in.unmPairCount);
