@@ -110,13 +110,14 @@ struct Params {
 //     (cyclic extension, so that a lane's address is linear in the read base index),
 //     C[5][Lg] countsGap, NC[5][Lg] new_counts_gap, G[rows] gapString codes,
 //     PREV[Lg] previous hard consensus
-//   local region (always shared): ME[k] = e, MT2[k] = {1-e-ins-del, e}, ETP[25], then per chunk of reads RC (codes) and W.
-struct Plan { int S, rows, oUT, oC, oNC, oG, oPREV, tableBytes, oME, oMT2, oETP, localFixed, maxLenPad, nMax, perRead; };
+//   local region (always shared): ME[k] = e, MER[i] = e[modelLen-1-i] (reverse-strand reads walk it forwards), MT2[k] = {1-e-ins-del, e},
+//   ETP[25], then per chunk of reads the records, RC (codes), RC2 (code * S: plane offset of the walk) and W.
+struct Plan { int S, rows, oUT, oC, oNC, oG, oPREV, tableBytes, oME, oMER, oMT2, oETP, localFixed, maxLenPad, nMax, perRead; };
 __host__ __device__ inline int al16(int x) { return (x + 15) & ~15; }
 __host__ __device__ inline Plan makePlan(int Lg, int F, int modelLen, int maxLen, int mode, int bandMax) {
     Plan p;
     p.maxLenPad = (maxLen + 15) & ~15;
-    p.S = Lg + p.maxLenPad; p.rows = Lg + 2 * F;
+    p.S = (Lg + p.maxLenPad + 7) & ~7; p.rows = Lg + 2 * F;      // plane stride: a multiple of 8 entries (RC2 stores code * S / 8 in 16 bits)
     int o = 0;
     p.oUT = o; o += 16 * 5 * p.S;
     p.oC = o; o += 8 * 5 * Lg;
@@ -127,13 +128,14 @@ __host__ __device__ inline Plan makePlan(int Lg, int F, int modelLen, int maxLen
     if (p.tableBytes < 12 * kThreads) p.tableBytes = al16(12 * kThreads);     // the prologue's prefix-sum scratch lives here
     o = 0;
     p.oME = o; o += al16(8 * modelLen);
+    p.oMER = o; o += al16(8 * modelLen);
     p.oMT2 = o; o += 16 * modelLen;
     p.oETP = o; o += 208;
     p.localFixed = al16(o);
     int n = (mode == FB_MODE_UNMAPPED) ? (maxLen + Lg - 1) : (maxLen - 1);
     if (mode == FB_MODE_UNMAPPED && bandMax < n) n = bandMax;     // unmapped reads always pass through the insert-size filter
     p.nMax = n > 1 ? n : 1;
-    p.perRead = 8 * p.nMax + p.maxLenPad + 56;       // weights + codes + record + threshold + unit counters
+    p.perRead = 8 * p.nMax + 3 * p.maxLenPad + 56;   // weights + codes (bytes and plane offsets) + record + threshold + unit counters
     return p;
 }
 
@@ -274,6 +276,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
     unsigned char* const G = tbase + pl.oG;
     unsigned char* const PREV = tbase + pl.oPREV;
     double* const ME = (double*)(lbase + pl.oME);
+    double* const MER = (double*)(lbase + pl.oMER);
     double2* const MT2 = (double2*)(lbase + pl.oMT2);
     double* const ETP = (double*)(lbase + pl.oETP);
     unsigned char* const chunkBase = lbase + pl.localFixed;
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
     int comp = 0;          // comp_count (Figbird.cpp:3919-3927), kept identically by every thread
     bool gChanged = true;  // the gap string differs from the one the cached pass-2 thresholds were computed on
     // ---- model tables, flank part of the gap string
-    for (int k = tid; k < m.max_read_len; k += kThreads) { const double e = m.e[k]; ME[k] = e; MT2[k] = make_double2(m.match[k], e); }
+    for (int k = tid; k < m.max_read_len; k += kThreads) { const double e = m.e[k]; ME[k] = e; MER[m.max_read_len - 1 - k] = e; MT2[k] = make_double2(m.match[k], e); }
     if (tid < 25) ETP[tid] = m.etp[tid];
     for (int r = tid; r < rows; r += kThreads) {
         const int x = r - F;
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
         sumTerms = (long long)s_terms;
     }
     const int totalW = (int)sumN;
-    const bool singleChunk = (8LL * totalW + (long long)R * (mlp + 56) + 96) <= (long long)chunkBytes;
+    const bool singleChunk = (8LL * totalW + (long long)R * (3 * mlp + 56) + 96) <= (long long)chunkBytes;
     int prevValid = 0;   // previous hard consensus present (uniform)
 
     auto storeRow = [&](int x, const double p[4], const double e[5]) {     // gap row x and its cyclic copies
@@ -384,14 +387,15 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
     struct RMeta { int xlo, wrel, n, packed, rel, u1, u2, x1; };     // packed = len | jlo<<8 | jhi<<16 | flags<<24; wrel/u1/u2 relative to the chunk
     RMeta* const RM = (RMeta*)chunkBase;
     int nqCur = 0;                       // reads in the resident chunk (uniform)
-    double* THR = nullptr; int* CNT = nullptr; int* X1P = nullptr; unsigned char* RC = nullptr; double* W = nullptr;
+    double* THR = nullptr; int* CNT = nullptr; int* X1P = nullptr; unsigned char* RC = nullptr; unsigned short* RC2 = nullptr; double* W = nullptr;
     auto carveChunk = [&](int nq) {
         nqCur = nq;
         THR = (double*)(chunkBase + 32 * (size_t)(nq + 1));      // exact pass-2 product at X1P (pruning threshold)
         CNT = (int*)((unsigned char*)THR + al16(8 * nq));        // [2][nq] finished pass-1 / pass-2 units of a read
         X1P = CNT + 2 * nq;                                      // offset THR was computed at
         RC = (unsigned char*)CNT + al16(12 * nq);
-        W = (double*)(RC + (size_t)nq * mlp);
+        RC2 = (unsigned short*)(RC + (size_t)nq * mlp);         // [nq][mlp] code * S / 8: plane offset of the walk in units of 8 entries
+        W = (double*)(RC + (size_t)nq * 3 * mlp);
     };
     auto stageReads = [&](int q0, int q1) {   // read records and codes of the chunk
         const int nq = q1 - q0;
@@ -413,7 +417,8 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
         for (int i = tid; i < n; i += kThreads) {
             const int ql = i / mlp, j = i - ql * mlp;
             const int qi = g.read_begin + q0 + ql;
-            RC[i] = (j < prm.read_len[qi]) ? prm.codes[prm.read_off[qi] + j] : (unsigned char)4;
+            const unsigned char c = (j < prm.read_len[qi]) ? prm.codes[prm.read_off[qi] + j] : (unsigned char)4;
+            RC[i] = c; RC2[i] = (unsigned short)(c * (S >> 3));
         }
     };
     // reads [q0, q1) whose records + codes + weight rows fit the chunk region (at least one read)
@@ -422,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
         __syncthreads();
         if (tid == 0) {
             int q = q0; long long bytes = 96;
-            while (q < R) { const long long nb = 8LL * (mt.woff[q + 1] - mt.woff[q]) + mlp + 56; if (q > q0 && bytes + nb > chunkBytes) break; bytes += nb; q++; }
+            while (q < R) { const long long nb = 8LL * (mt.woff[q + 1] - mt.woff[q]) + 3 * mlp + 56; if (q > q0 && bytes + nb > chunkBytes) break; bytes += nb; q++; }
             s_q1 = q;
         }
         __syncthreads();
@@ -679,9 +684,8 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                     int x0cur = xm - m0 * Lg;          // placement whose segment contains read base js
                     int jw = (m0 + 1) * Lg - xm;       // read base at which the walk re-enters gap row 0 (> js)
                     const double2* ptr = UT + xm;      // + j: cyclically extended table, plane 0
-                    const unsigned char* rc = RC + ql * mlp;
-                    const double* me = ME; int kstep = 1, kb = 0;
-                    if ((r.packed >> 24) & FB_READ_REVERSE) { kb = len - 1; kstep = -1; }
+                    const unsigned short* rc = RC2 + ql * mlp;
+                    const double* me = ((r.packed >> 24) & FB_READ_REVERSE) ? MER + (m.max_read_len - len) : ME;     // me[j] = e of read base j
                     double acc = 1.0, save = 1.0;
                     const bool oneWrap = (je - js) <= Lg;     // a lane re-enters row 0 at most once: keep the first product in a register
                     auto mul = [&](const double2 v, double e) { acc = __dmul_rn(acc, __fma_rn(e, v.y, v.x)); };
@@ -695,18 +699,18 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                     // read bases [j, stop): MODE 0 = no lane wraps in this stretch, 1 = single-wrap lanes, 2 = general
                     auto run = [&](auto MODE, int& j, int stop) {
                         auto wr = [&](int jj) { if (MODE.value == 1) wrap1(jj); else if (MODE.value == 2) wrapN(jj); };
-                        for (; j < stop && (j & 3); j++) { wr(j); mul(ptr[rc[j] * S + j], me[kb + kstep * j]); }
+                        for (; j < stop && (j & 3); j++) { wr(j); mul(ptr[rc[j] * 8 + j], me[j]); }
                         for (; j + 4 <= stop; j += 4) {
-                            const unsigned cw = *(const unsigned*)(rc + j);
+                            const uint2 cw = *(const uint2*)(rc + j);        // four plane offsets
                             const double2* pj = ptr + j;
-                            const double2 v0 = pj[(cw & 0xff) * S], v1 = pj[((cw >> 8) & 0xff) * S + 1], v2 = pj[((cw >> 16) & 0xff) * S + 2], v3 = pj[(cw >> 24) * S + 3];
-                            const double e0 = me[kb + kstep * j], e1 = me[kb + kstep * (j + 1)], e2 = me[kb + kstep * (j + 2)], e3 = me[kb + kstep * (j + 3)];
+                            const double2 v0 = pj[(cw.x & 0xffff) * 8], v1 = pj[(cw.x >> 16) * 8 + 1], v2 = pj[(cw.y & 0xffff) * 8 + 2], v3 = pj[(cw.y >> 16) * 8 + 3];
+                            const double e0 = me[j], e1 = me[j + 1], e2 = me[j + 2], e3 = me[j + 3];
                             wr(j); mul(v0, e0);
                             wr(j + 1); mul(v1, e1);
                             wr(j + 2); mul(v2, e2);
                             wr(j + 3); mul(v3, e3);
                         }
-                        for (; j < stop; j++) { wr(j); mul(ptr[rc[j] * S + j], me[kb + kstep * j]); }
+                        for (; j < stop; j++) { wr(j); mul(ptr[rc[j] * 8 + j], me[j]); }
                     };
                     // lanes hold consecutive diagonals, so their wrap points fill a window of at most 32 consecutive read bases per period
                     int wmin = __reduce_min_sync(0xffffffffu, jw), wmax = __reduce_max_sync(0xffffffffu, jw);
