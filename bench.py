@@ -264,7 +264,7 @@ def main():
             "e2e": {"value": ref_p1_all / dt_max, "unit": unit, "h2d_bytes_per_step": h2d / a.steps, "d2h_bytes_per_step": d2h / a.steps,
                     "note": "through fb_fillgaps_main: files -> model -> per-gap control on host threads -> engine; reference-equivalent pass-1 placements / wall",
                     "gaps_per_s": (len(open(os.path.join(case, "partial", "Temp", "gapInfo.txt")).readlines()) * world * a.steps) / dt_max,
-                    "host_seconds_per_step": {k: sum(m[k] for m in metrics) / a.steps for k in ("t_load", "t_model", "t_prepare", "t_fill", "t_write")}},
+                    "host_seconds_per_step": {k: sum(m[k] for m in metrics) / a.steps for k in ("t_load", "t_model", "t_prepare", "t_fill", "t_write", "t_ctx_upload", "t_workers", "t_engine_calls", "cpu_workers")}},
             "gpu_launches": int(launches_all), "device_placements_p1": dev_p1_all, "device_placements_p2": dev_p2_all, "roofline": roof}
     if world == 1 and not a.no_cpu_baseline and fc.have_reference():
         sample = prepare_case(os.path.join(base, "sample"), SAMPLE, 1102)

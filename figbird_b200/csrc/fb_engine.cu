@@ -701,9 +701,10 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                         auto wr = [&](int jj) { if (MODE.value == 1) wrap1(jj); else if (MODE.value == 2) wrapN(jj); };
                         for (; j < stop && (j & 3); j++) { wr(j); mul(ptr[rc[j] * 8 + j], me[j]); }
                         for (; j + 4 <= stop; j += 4) {
-                            const uint2 cw = *(const uint2*)(rc + j);        // four plane offsets
-                            const double2* pj = ptr + j;
-                            const double2 v0 = pj[(cw.x & 0xffff) * 8], v1 = pj[(cw.x >> 16) * 8 + 1], v2 = pj[(cw.y & 0xffff) * 8 + 2], v3 = pj[(cw.y >> 16) * 8 + 3];
+                            const uint2 cw = *(const uint2*)(rc + j);        // four plane offsets (units of 8 entries = 128 bytes)
+                            const unsigned char* pb = (const unsigned char*)(ptr + j);       // byte address: mask + shift-add per entry
+                            const double2 v0 = *(const double2*)(pb + ((cw.x & 0xffffu) << 7)), v1 = *(const double2*)(pb + ((cw.x >> 16) << 7) + 16),
+                                          v2 = *(const double2*)(pb + ((cw.y & 0xffffu) << 7) + 32), v3 = *(const double2*)(pb + ((cw.y >> 16) << 7) + 48);
                             const double e0 = me[j], e1 = me[j + 1], e2 = me[j + 2], e3 = me[j + 3];
                             wr(j); mul(v0, e0);
                             wr(j + 1); mul(v1, e1);
