@@ -703,8 +703,9 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                         for (; j + 4 <= stop; j += 4) {
                             const uint2 cw = *(const uint2*)(rc + j);        // four plane offsets (units of 8 entries = 128 bytes)
                             const unsigned char* pb = (const unsigned char*)(ptr + j);       // byte address: mask + shift-add per entry
-                            const double2 v0 = *(const double2*)(pb + ((cw.x & 0xffffu) << 7)), v1 = *(const double2*)(pb + ((cw.x >> 16) << 7) + 16),
-                                          v2 = *(const double2*)(pb + ((cw.y & 0xffffu) << 7) + 32), v3 = *(const double2*)(pb + ((cw.y >> 16) << 7) + 48);
+                            const unsigned o0 = __byte_perm(cw.x, 0, 0x4410), o1 = __byte_perm(cw.x, 0, 0x4432), o2 = __byte_perm(cw.y, 0, 0x4410), o3 = __byte_perm(cw.y, 0, 0x4432);
+                            const double2 v0 = *(const double2*)(pb + (o0 << 7)), v1 = *(const double2*)(pb + (o1 << 7) + 16),
+                                          v2 = *(const double2*)(pb + (o2 << 7) + 32), v3 = *(const double2*)(pb + (o3 << 7) + 48);
                             const double e0 = me[j], e1 = me[j + 1], e2 = me[j + 2], e3 = me[j + 3];
                             wr(j); mul(v0, e0);
                             wr(j + 1); mul(v1, e1);
