@@ -690,11 +690,18 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                     const bool oneWrap = (je - js) <= Lg;     // a lane re-enters row 0 at most once: keep the first product in a register
                     auto mul = [&](const double2 v, double e) { acc = __dmul_rn(acc, __fma_rn(e, v.y, v.x)); };
                     auto wrap1 = [&](int j) { const bool w = (j == jw); save = w ? acc : save; acc = w ? 1.0 : acc; };
+                    // general case (a lane re-enters row 0 several times, Lg < read length): branch-free, one predicated store.
+                    // slotN = x0cur - xlo for active lanes, out of range for inactive ones
+                    int slotN = active ? x0cur - xlo : -1;
+                    const int nAct = active ? n : 0;
                     auto wrapN = [&](int j) {
-                        if (j == jw) {      // the walk re-enters gap row 0: the running product belongs to placement x0cur
-                            if (active && (unsigned)(x0cur - xlo) < (unsigned)n) Wq[x0cur - xlo] = acc;
-                            acc = 1.0; x0cur -= Lg; jw += Lg;
-                        }
+                        const bool w = (j == jw);       // the walk re-enters gap row 0: the running product belongs to placement x0cur
+                        const bool st = w && ((unsigned)slotN < (unsigned)nAct);
+                        if (TSMEM) {
+                            const unsigned wa = (unsigned)__cvta_generic_to_shared(Wq) + ((unsigned)slotN << 3);
+                            asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p st.shared.f64 [%1], %2; }" :: "r"((unsigned)st), "r"(wa), "d"(acc) : "memory");
+                        } else if (st) Wq[slotN] = acc;
+                        acc = w ? 1.0 : acc; slotN = w ? slotN - Lg : slotN; x0cur = w ? x0cur - Lg : x0cur; jw = w ? jw + Lg : jw;
                     };
                     // read bases [j, stop): MODE 0 = no lane wraps in this stretch, 1 = single-wrap lanes, 2 = general
                     auto run = [&](auto MODE, int& j, int stop) {
