@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
     const int S = pl.S, rows = pl.rows, mlp = pl.maxLenPad;
 
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ int s_same[2], s_gchg, s_flags, s_q1, s_next1, s_next2;
+    __shared__ int s_same[2], s_gchg, s_flags, s_q1, s_next1, s_next2, s_tw[kWarps], s_task[kWarps + 1];
     __shared__ unsigned long long s_lane1, s_lane2, s_terms;
 
     unsigned char* const tbase = TSMEM ? smem : (prm.scratch + it.scratch_off);
@@ -608,7 +608,48 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
         // count matrix one after the other (fixed order), separated by barriers
         const int rowsPerThread = (Lg > 64) ? 4 : 2;
         const int nG = (Lg + rowsPerThread - 1) / rowsPerThread, tpp = (nG + 31) & ~31;
-        const int split = (Lg > 0 && tpp <= kThreads) ? max(1, kThreads / tpp) : 1;     // parts of the reads per row tile
+        // A warp = one tile of 32 * rowsPerThread rows and one part of the reads.  The warps are dealt to the tiles in
+        // proportion to the tiles' work (read bases walked), computed once from the admissible bands.
+        const int nTiles = tpp >> 5;
+        const bool tiled = Lg > 0 && nTiles <= kWarps;
+        int split = 1;                 // longest chain of parts (uniform)
+        int myTile = 0, myPart = 0, myParts = 1; bool myIdle = false;
+        if (tiled) {
+            if (warp < nTiles) {
+                const int xw0 = warp * 32 * rowsPerThread, xw1 = min(Lg - 1, xw0 + 32 * rowsPerThread - 1);
+                int w = 0;
+                for (int q = lane; q < R; q += 32) {
+                    const int n = mt.woff[q + 1] - mt.woff[q];
+                    if (n <= 0) continue;
+                    const int xlo = mt.xlo[q], len = prm.read_len[g.read_begin + q];
+                    const int ja = max(0, xw0 - xlo - n + 1), jb = min(len - 1, xw1 - xlo);
+                    w += max(0, jb - ja + 1);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+                if (lane == 0) s_tw[warp] = w + 1;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int parts[kWarps];
+                for (int t = 0; t < nTiles; t++) parts[t] = 1;
+                const int cap = max(1, R);     // more parts than reads is useless
+                for (int used = nTiles; used < kWarps; used++) {
+                    int bt = -1;
+                    for (int t = 0; t < nTiles; t++) if (parts[t] < cap && (bt < 0 || (long long)s_tw[t] * parts[bt] > (long long)s_tw[bt] * parts[t])) bt = t;
+                    if (bt < 0) break;
+                    parts[bt]++;
+                }
+                int w = 0, mp = 1;
+                for (int t = 0; t < nTiles; t++) { for (int p = 0; p < parts[t]; p++) s_task[w++] = t | (p << 8) | (parts[t] << 16); mp = max(mp, parts[t]); }
+                for (; w < kWarps; w++) s_task[w] = 0xff;
+                s_task[kWarps] = mp;
+            }
+            __syncthreads();
+            const int task = s_task[warp];
+            myIdle = (task & 0xff) == 0xff; myTile = task & 0xff; myPart = (task >> 8) & 0xff; myParts = max(1, (task >> 16) & 0xff);
+            split = s_task[kWarps];
+        }
         for (int call = 0; call < maxCalls; call++) {
             const bool extra = emDone;
             const int slot = (it.flags & FB_FLAG_RECORD_ALL) ? call : 0;
@@ -768,8 +809,10 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                 // per step slides through four registers.
                 auto gather = [&](auto BB) {
                     constexpr int B = BB.value;           // gap rows per thread
-                    for (int idx = tid; idx < tpp * split || split > 1; idx += kThreads) {
-                        const int s = idx / tpp, gi = idx - s * tpp;      // split > 1: one trip, every thread reaches the barriers below
+                    for (int idx = tid; idx < tpp || tiled; idx += kThreads) {
+                        // tiled: one trip, every thread reaches the barriers below; else a loop over the row groups, all reads
+                        const int s = tiled ? myPart : 0, stride = tiled ? myParts : 1;
+                        const int gi = tiled ? myTile * 32 + lane : idx;
                         const int x = gi * B;
                         const int xw0 = (gi - lane) * B, xw1 = min(Lg - 1, xw0 + 32 * B - 1);      // rows of this warp
                         double a[B][5];
@@ -777,7 +820,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                         for (int b = 0; b < B; b++)
 #pragma unroll
                             for (int k = 0; k < 5; k++) a[b][k] = 0.0;
-                        if (xw0 < Lg && s < split) for (int ql = s; ql < nq; ql += split) {
+                        if (xw0 < Lg && !(tiled && myIdle)) for (int ql = s; ql < nq; ql += stride) {
                             const RMeta r = RM[ql];
                             if (r.n <= 0) continue;
                             const int len = r.packed & 0xff;
@@ -840,7 +883,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                             }
                         }
                         for (int sp = 0; sp < split; sp++) {
-                            if (sp == s && gi < nG) {
+                            if (sp == s && gi < nG && !(tiled && myIdle)) {
 #pragma unroll
                                 for (int b = 0; b < B; b++) {
                                     const int row = x + b;
@@ -850,9 +893,9 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                                     }
                                 }
                             }
-                            if (split > 1) __syncthreads();
+                            if (tiled) __syncthreads();
                         }
-                        if (split > 1) break;
+                        if (tiled) break;
                     }
                 };
                 if (rowsPerThread == 4) gather(std::integral_constant<int, 4>()); else gather(std::integral_constant<int, 2>());
