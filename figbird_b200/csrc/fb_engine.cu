@@ -58,6 +58,9 @@ namespace {
 #ifndef FB_CTAS
 #define FB_CTAS 2
 #endif
+#ifndef FB_PHASES
+#define FB_PHASES 0     // 1: thread 0 accumulates the clock cycles between the barriers of an EM round (diagnostic build)
+#endif
 #ifndef FB_FUSE1
 #define FB_FUSE1 0      // 1: the warp that completes a read's last pass-1 unit finishes the read inside the unit loop
 #endif
@@ -120,7 +123,7 @@ __host__ __device__ inline Plan makePlan(int Lg, int F, int modelLen, int maxLen
     p.S = (Lg + p.maxLenPad + 7) & ~7; p.rows = Lg + 2 * F;      // plane stride: a multiple of 8 entries (RC2 stores code * S / 8 in 16 bits)
     int o = 0;
     p.oUT = o; o += 16 * 5 * p.S;
-    p.oC = o; o += 8 * 5 * Lg;
+    p.oC = o; o += 8 * 5 * ((Lg + 3) & ~3);
     p.oNC = o; o += 4 * 5 * Lg;
     p.oG = o; o += al16(p.rows);
     p.oPREV = o; o += al16(Lg);
@@ -140,12 +143,12 @@ __host__ __device__ inline Plan makePlan(int Lg, int F, int modelLen, int maxLen
 }
 
 // Per-read metadata of one item (global scratch, written in the prologue): R+1 entries each.
-struct Meta { int* xlo; int* woff; int* u1; int* u2; int* x1; double* thr; };
-__host__ __device__ inline size_t metaBytes(int R) { return (size_t)al16(4 * (R + 1)) * 5 + (size_t)al16(8 * (R + 1)); }
+struct Meta { int* xlo; int* nn; int* woff; int* u1; int* u2; int* x1; double* thr; };
+__host__ __device__ inline size_t metaBytes(int R) { return (size_t)al16(4 * (R + 1)) * 6 + (size_t)al16(8 * (R + 1)); }
 __device__ __forceinline__ Meta carveMeta(unsigned char* base, int R) {
     Meta m; const size_t s = (size_t)al16(4 * (R + 1));
     m.xlo = (int*)base; m.woff = (int*)(base + s); m.u1 = (int*)(base + 2 * s); m.u2 = (int*)(base + 3 * s); m.x1 = (int*)(base + 4 * s);
-    m.thr = (double*)(base + 5 * s);
+    m.nn = (int*)(base + 5 * s); m.thr = (double*)(base + 6 * s);
     return m;
 }
 
@@ -175,6 +178,13 @@ __device__ __forceinline__ void band(const DevModel& m, const DevGap& g, int fl,
     const long long l2 = a > lo ? a : lo, h2 = b < hi ? b : hi;
     if (l2 > h2) { *xlo = lo; *xhi = lo - 1; } else { *xlo = (int)l2; *xhi = (int)h2; }
 }
+
+// Pass-1 weight rows are stored in four planes by (placement index mod 4): the gather's lanes own 4 consecutive gap rows each,
+// so at any read base they need indices 4*lane + const -- one plane, consecutive entries, no bank conflicts.
+#ifndef FB_WTR
+#define FB_WTR 0
+#endif
+__device__ __forceinline__ int wtr(int i, int np) { return FB_WTR ? (i & 3) * np + (i >> 2) : i; }
 
 // E[j] = sum_{k<4, k!=j} P[k]*ETP[k][j] in k order (Figbird.cpp:2118-2137)
 __device__ __forceinline__ void errRow(const double* etp, const double p[4], double e[5]) {
@@ -261,17 +271,24 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
     const int Lg = it.Lg, F = g.flank_len, R = g.n_reads;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool unm = (g.mode == FB_MODE_UNMAPPED);
+#if FB_PHASES
+    long long ph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long phLast = clock64();
+#define PHASE(k) do { if (tid == 0) { const long long t_ = clock64(); ph[k] += t_ - phLast; phLast = t_; } } while (0)
+#else
+#define PHASE(k) do { } while (0)
+#endif
     const Plan pl = makePlan(Lg, F, m.max_read_len, it.max_len, g.mode, m.tmax - m.tmin + 1);
     const int S = pl.S, rows = pl.rows, mlp = pl.maxLenPad;
 
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_same[2], s_gchg, s_flags, s_q1, s_next1, s_next2, s_tw[kWarps], s_task[kWarps + 1];
-    __shared__ unsigned long long s_lane1, s_lane2, s_terms;
+    __shared__ unsigned long long s_lane1, s_lane2, s_terms, s_nsum;
 
     unsigned char* const tbase = TSMEM ? smem : (prm.scratch + it.scratch_off);
     unsigned char* const lbase = TSMEM ? smem + pl.tableBytes : smem;
     double2* const UT = (double2*)(tbase + pl.oUT);
     double* const C = (double*)(tbase + pl.oC);
+    const int LgC = (Lg + 3) & ~3;      // plane stride of C: rows x..x+3 of a gather thread are two aligned 16-byte pairs
     int* const NC = (int*)(tbase + pl.oNC);
     unsigned char* const G = tbase + pl.oG;
     unsigned char* const PREV = tbase + pl.oPREV;
@@ -294,7 +311,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
     const unsigned char* lf = prm.flank + g.flank_begin;
     const unsigned char* rf = lf + F;
 
-    if (tid == 0) { s_same[0] = 1; s_same[1] = 1; s_gchg = 0; s_next1 = 0; s_next2 = 0; s_flags = 0; s_lane1 = 0; s_lane2 = 0; s_terms = 0; }
+    if (tid == 0) { s_same[0] = 1; s_same[1] = 1; s_gchg = 0; s_next1 = 0; s_next2 = 0; s_flags = 0; s_lane1 = 0; s_lane2 = 0; s_terms = 0; s_nsum = 0; }
     int comp = 0;          // comp_count (Figbird.cpp:3919-3927), kept identically by every thread
     bool gChanged = true;  // the gap string differs from the one the cached pass-2 thresholds were computed on
     // ---- model tables, flank part of the gap string
@@ -317,30 +334,31 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
             const int len = prm.read_len[qi];
             int xlo, xhi; band(m, g, prm.read_flags[qi], prm.read_mate[qi], len, Lg, finRef, &xlo, &xhi);
             const int n = xhi - xlo + 1;
-            mt.xlo[q] = xlo; mt.woff[q] = n;
-            sw += n; s1 += (Lg > 0) ? ((n < Lg ? n : Lg) + 31) / 32 : 0; s2 += (n + 63) / 64;
+            mt.xlo[q] = xlo; mt.nn[q] = n;
+            sw += (n + 3) & ~3; s1 += (Lg > 0) ? ((n < Lg ? n : Lg) + 31) / 32 : 0; s2 += (n + 63) / 64;
             st += (long long)n * (len - prm.read_jcut[qi] - prm.read_jlo[qi]);
         }
         int* const s_scan = (int*)UT;          // [3][kThreads] scratch: the row tables are written after this block
         s_scan[tid] = sw; s_scan[kThreads + tid] = s1; s_scan[2 * kThreads + tid] = s2;
         if (st) atomicAdd(&s_terms, (unsigned long long)st);
+        if (qe > qb) { long long ns = 0; for (int q = qb; q < qe; q++) ns += mt.nn[q]; atomicAdd(&s_nsum, (unsigned long long)ns); }
         __syncthreads();
         if (tid < 3) { int acc = 0; for (int i = 0; i < kThreads; i++) { const int v = s_scan[tid * kThreads + i]; s_scan[tid * kThreads + i] = acc; acc += v; } }
         __syncthreads();
         sw = s_scan[tid]; s1 = s_scan[kThreads + tid]; s2 = s_scan[2 * kThreads + tid];
         for (int q = qb; q < qe; q++) {
-            const int n = mt.woff[q];
+            const int n = mt.nn[q];
             mt.woff[q] = sw; mt.u1[q] = s1; mt.u2[q] = s2;
-            sw += n; s1 += (Lg > 0) ? ((n < Lg ? n : Lg) + 31) / 32 : 0; s2 += (n + 63) / 64;
+            sw += (n + 3) & ~3; s1 += (Lg > 0) ? ((n < Lg ? n : Lg) + 31) / 32 : 0; s2 += (n + 63) / 64;
         }
         // entry R of each prefix array: written by the thread that owns the last read (thread 0 when R == 0)
         const int lastOwner = (R > 0) ? (R - 1) / per : 0;
-        if (tid == lastOwner) { mt.woff[R] = sw; mt.u1[R] = s1; mt.u2[R] = s2; }
+        if (tid == lastOwner) { mt.woff[R] = sw; mt.u1[R] = s1; mt.u2[R] = s2; mt.nn[R] = 0; }
         __syncthreads();
-        sumN = mt.woff[R];
+        sumN = (long long)s_nsum;
         sumTerms = (long long)s_terms;
     }
-    const int totalW = (int)sumN;
+    const int totalW = mt.woff[R];
     const bool singleChunk = (8LL * totalW + (long long)R * (3 * mlp + 56) + 96) <= (long long)chunkBytes;
     int prevValid = 0;   // previous hard consensus present (uniform)
 
@@ -355,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
     if (it.kind == FB_ITEM_EM) {
         if (it.flags & FB_FLAG_RESUME) {
             const double* cin = (const double*)(prm.in_arena + it.counts_in_off);
-            for (int i = tid; i < 5 * Lg; i += kThreads) { int x = i / 5, k = i % 5; C[k * Lg + x] = cin[i]; }
+            for (int i = tid; i < 5 * Lg; i += kThreads) { int x = i / 5, k = i % 5; C[k * LgC + x] = cin[i]; }
             if (it.string_in_off >= 0) { const unsigned char* sin = prm.in_arena + it.string_in_off; for (int x = tid; x < Lg; x += kThreads) PREV[x] = sin[x]; prevValid = 1; }
             comp = it.comp_in;
         } else {
@@ -407,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
             r.wrel = mt.woff[q] - wb; r.u1 = mt.u1[q] - u1b; r.u2 = mt.u2[q] - u2b;
             if (ql < nq) {
                 const int qi = g.read_begin + q; const int len = prm.read_len[qi];
-                r.xlo = mt.xlo[q]; r.n = mt.woff[q + 1] - mt.woff[q]; r.rel = prm.read_mate[qi]; r.x1 = mt.x1[q];
+                r.xlo = mt.xlo[q]; r.n = mt.nn[q]; r.rel = prm.read_mate[qi]; r.x1 = mt.x1[q];
                 r.packed = len | (prm.read_jlo[qi] << 8) | ((len - prm.read_jcut[qi]) << 16) | (prm.read_flags[qi] << 24);
             } else { r.xlo = 0; r.n = 0; r.rel = 0; r.x1 = INT_MIN; r.packed = 0; }
             RM[ql] = r;
@@ -449,7 +467,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
         {
             double c[5];
 #pragma unroll
-            for (int k = 0; k < 5; k++) c[k] = C[k * Lg + x];
+            for (int k = 0; k < 5; k++) c[k] = C[k * LgC + x];
             double total = 0;
 #pragma unroll
             for (int k = 0; k < 5; k++) total = __dadd_rn(total, c[k]);
@@ -507,6 +525,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                 THR[ql] = thr; X1P[ql] = r.x1;
             }
             __syncthreads();
+            PHASE(6);
             // first maximum over ascending offsets (strict >), accept test, unit votes (Figbird.cpp:3787-3912): by one warp
             auto finishRead2 = [&](int ql) {
                 const RMeta r = RM[ql];
@@ -590,9 +609,11 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
             for (int ql = warp; ql < nq; ql += kWarps) if (RM[ql + 1].u2 == RM[ql].u2) finishRead2(ql);      // reads without offsets
 #else
             __syncthreads();
+            PHASE(7);
             for (int ql = warp; ql < nq; ql += kWarps) finishRead2(ql);
 #endif
             __syncthreads();
+            PHASE(8);
         }
     };
 
@@ -619,7 +640,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                 const int xw0 = warp * 32 * rowsPerThread, xw1 = min(Lg - 1, xw0 + 32 * rowsPerThread - 1);
                 int w = 0;
                 for (int q = lane; q < R; q += 32) {
-                    const int n = mt.woff[q + 1] - mt.woff[q];
+                    const int n = mt.nn[q];
                     if (n <= 0) continue;
                     const int xlo = mt.xlo[q], len = prm.read_len[g.read_begin + q];
                     const int ja = max(0, xw0 - xlo - n + 1), jb = min(len - 1, xw1 - xlo);
@@ -650,11 +671,13 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
             myIdle = (task & 0xff) == 0xff; myTile = task & 0xff; myPart = (task >> 8) & 0xff; myParts = max(1, (task >> 16) & 0xff);
             split = s_task[kWarps];
         }
+        PHASE(0);
         for (int call = 0; call < maxCalls; call++) {
             const bool extra = emDone;
             const int slot = (it.flags & FB_FLAG_RECORD_ALL) ? call : 0;
             // (no barrier of its own: the walk does not touch C / NC, and a barrier separates it from the gather)
-            for (int i = tid; i < 5 * Lg; i += kThreads) { C[i] = 0.0; NC[i] = 0; }
+            for (int i = tid; i < 5 * LgC; i += kThreads) C[i] = 0.0;
+            for (int i = tid; i < 5 * Lg; i += kThreads) NC[i] = 0;
             if (tid == 0) { s_same[call & 1] = 1; s_gchg = 0; }      // (the other parity may still be read by slow warps of the previous round)
             // ================= pass 1 (Figbird.cpp:3082-3263, 3530-3689) =================
             for (int q0 = 0, q1; q0 < R; q0 = q1) {
@@ -669,6 +692,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                     const int len = r.packed & 0xff, jlo = (r.packed >> 8) & 0xff, jhi = (r.packed >> 16) & 0xff, fl = (r.packed >> 24) & 0xff;
                     const int xlo = r.xlo, n = r.n, rel = r.rel;
                     double* const Wq = W + r.wrel;
+                    const int np = (n + 3) >> 2;
                     const double* LF = prm.lfrf + 2 * prm.read_off[qi];
                     const double* RF = LF + len;
                     double best = 0.0; int bestI = 0x7fffffff;
@@ -680,12 +704,12 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                             p = m.pdf[min(max((int)t, 0), m.n_insert - 1)];
                         }
                         if (x0 < 0) p = __dmul_rn(p, LF[-x0]);
-                        if (min(jhi, Lg - x0) > max(jlo, -x0)) p = __dmul_rn(p, Wq[i]);
+                        if (min(jhi, Lg - x0) > max(jlo, -x0)) p = __dmul_rn(p, Wq[wtr(i, np)]);
                         const int b = x0 + len - Lg;
                         if (b > 0) p = __dmul_rn(p, RF[b]);
                         double w = 0.0;
                         if (p > 0.0) w = placementWeight(p, unm); else p = 0.0;
-                        Wq[i] = w;
+                        Wq[wtr(i, np)] = w;
                         if (p > best) { best = p; bestI = i; }
                     }
 #pragma unroll
@@ -711,6 +735,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                     const int len = r.packed & 0xff, jlo = (r.packed >> 8) & 0xff, jhi = (r.packed >> 16) & 0xff;
                     const int xlo = r.xlo, n = r.n;
                     double* const Wq = W + r.wrel;
+                    const int np = (n + 3) >> 2;
                     const bool full = n >= Lg;
                     const int nl = full ? Lg : n;
                     const int idx = uu * 32 + lane;
@@ -739,9 +764,9 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                         const bool w = (j == jw);       // the walk re-enters gap row 0: the running product belongs to placement x0cur
                         const bool st = w && ((unsigned)slotN < (unsigned)nAct);
                         if (TSMEM) {
-                            const unsigned wa = (unsigned)__cvta_generic_to_shared(Wq) + ((unsigned)slotN << 3);
+                            const unsigned wa = (unsigned)__cvta_generic_to_shared(Wq) + ((unsigned)wtr(slotN, np) << 3);
                             asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p st.shared.f64 [%1], %2; }" :: "r"((unsigned)st), "r"(wa), "d"(acc) : "memory");
-                        } else if (st) Wq[slotN] = acc;
+                        } else if (st) Wq[wtr(slotN, np)] = acc;
                         acc = w ? 1.0 : acc; slotN = w ? slotN - Lg : slotN; x0cur = w ? x0cur - Lg : x0cur; jw = w ? jw + Lg : jw;
                     };
                     // read bases [j, stop): MODE 0 = no lane wraps in this stretch, 1 = single-wrap lanes, 2 = general
@@ -772,9 +797,9 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                         if (active) {
                             const bool wrapped = jw < je;
                             if (wrapped) {
-                                if ((unsigned)(x0cur - xlo) < (unsigned)n) Wq[x0cur - xlo] = save;
-                                if ((unsigned)(x0cur - Lg - xlo) < (unsigned)n) Wq[x0cur - Lg - xlo] = acc;
-                            } else if ((unsigned)(x0cur - xlo) < (unsigned)n) Wq[x0cur - xlo] = acc;
+                                if ((unsigned)(x0cur - xlo) < (unsigned)n) Wq[wtr(x0cur - xlo, np)] = save;
+                                if ((unsigned)(x0cur - Lg - xlo) < (unsigned)n) Wq[wtr(x0cur - Lg - xlo, np)] = acc;
+                            } else if ((unsigned)(x0cur - xlo) < (unsigned)n) Wq[wtr(x0cur - xlo, np)] = acc;
                         }
                     } else {
                         while (j < je) {
@@ -782,7 +807,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                             run(std::integral_constant<int, 2>(), j, min(je, wmax + 1));
                             wmin += Lg; wmax += Lg;
                         }
-                        if (active && (unsigned)(x0cur - xlo) < (unsigned)n) Wq[x0cur - xlo] = acc;
+                        if (active && (unsigned)(x0cur - xlo) < (unsigned)n) Wq[wtr(x0cur - xlo, np)] = acc;
                     }
                     if (lane == 0) atomicAdd(&s_lane1, (unsigned long long)(je - js) * 32ull);
                     }
@@ -799,9 +824,11 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                 for (int ql = warp; ql < nq; ql += kWarps) if (Lg <= 0 || RM[ql + 1].u1 == RM[ql].u1) finishRead1(ql);      // reads without gap-row units
 #else
                 __syncthreads();
+                PHASE(1);
                 for (int ql = warp; ql < nq; ql += kWarps) finishRead1(ql);
 #endif
                 __syncthreads();
+                PHASE(2);
                 if (tid == 0) s_next1 = 0;      // every warp has left the unit loop; the next one starts after further barriers
                 // ---- gather the weights of this chunk into the gap rows in a fixed order (deterministic, no FP atomics).
                 // A thread owns 4 consecutive rows x..x+3 and one part of the reads; all lanes of a warp walk the same read
@@ -830,7 +857,8 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                             if (ja > jb) continue;
                             const unsigned char* rc = RC + ql * mlp;
                             const double* wr = W + r.wrel;
-                            auto ld = [&](int i) -> double { return ((unsigned)i < (unsigned)n) ? wr[i] : 0.0; };
+                            const int np = (n + 3) >> 2;
+                            auto ld = [&](int i) -> double { return ((unsigned)i < (unsigned)n) ? wr[wtr(i, np)] : 0.0; };
                             int i0 = x - ja - xlo;                 // weight index of row x at read base ja; row x+b: i0 + b
                             double w[B];
 #pragma unroll
@@ -884,33 +912,37 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                         }
                         for (int sp = 0; sp < split; sp++) {
                             if (sp == s && gi < nG && !(tiled && myIdle)) {
+                                // rows x .. x+B-1 (x a multiple of B, planes padded to a multiple of 4): aligned pairs, rows beyond Lg are padding
 #pragma unroll
-                                for (int b = 0; b < B; b++) {
-                                    const int row = x + b;
-                                    if (row < Lg) {
+                                for (int k = 0; k < 5; k++)
 #pragma unroll
-                                        for (int k = 0; k < 5; k++) C[k * Lg + row] = __dadd_rn(C[k * Lg + row], a[b][k]);
+                                    for (int b = 0; b < B; b += 2) {
+                                        double2* cp = (double2*)(C + k * LgC + x + b);
+                                        double2 v = *cp;
+                                        v.x = __dadd_rn(v.x, a[b][k]); v.y = __dadd_rn(v.y, a[b + 1][k]);
+                                        *cp = v;
                                     }
-                                }
                             }
-                            if (tiled) __syncthreads();
+                            if (tiled) { __syncthreads(); if (sp == 0) PHASE(3); }
                         }
                         if (tiled) break;
                     }
                 };
                 if (rowsPerThread == 4) gather(std::integral_constant<int, 4>()); else gather(std::integral_constant<int, 2>());
                 __syncthreads();
+                PHASE(4);
             }
             // ================= computeSequence(0,0) =================
             for (int x = tid; x < Lg; x += kThreads) {
                 double mx = 0; int mi = -1;
 #pragma unroll
-                for (int k = 0; k < 5; k++) { double v = C[k * Lg + x]; if (v > mx) { mx = v; mi = k; } }
+                for (int k = 0; k < 5; k++) { double v = C[k * LgC + x]; if (v > mx) { mx = v; mi = k; } }
                 unsigned char c = (mi >= 0 && mi < 4) ? (unsigned char)mi : 4;
                 if (call == 0 || G[F + x] != c) s_gchg = 1;      // benign race: all writers store 1
                 G[F + x] = c; oSoft[x] = c;
             }
             __syncthreads();
+            PHASE(5);
             gChanged = (call == 0) || (s_gchg != 0);
             // ================= pass 2 =================
             pass2(slot, true);
@@ -935,6 +967,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
             }
             calls++;
             __syncthreads();
+            PHASE(9);
             if (unm) {
                 // an empty previous string equals the new one only when Lg == 0
                 const int equal = (Lg == 0) ? 1 : (prevValid && s_same[call & 1]);
@@ -948,7 +981,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
         }
         if (it.off_counts >= 0) {
             double* oc = (double*)(out + it.off_counts);
-            for (int i = tid; i < 5 * Lg; i += kThreads) { int x = i / 5, k = i % 5; oc[i] = C[k * Lg + x]; }
+            for (int i = tid; i < 5 * Lg; i += kThreads) { int x = i / 5, k = i % 5; oc[i] = C[k * LgC + x]; }
         }
     }
     __syncthreads();
@@ -959,6 +992,11 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
         atomicAdd(&prm.counters[0], (unsigned long long)(sumN * p1calls)); atomicAdd(&prm.counters[1], (unsigned long long)(sumN * calls));
         atomicAdd(&prm.counters[2], (unsigned long long)(sumTerms * (p1calls + calls)));
         atomicAdd(&prm.counters[3], s_lane1); atomicAdd(&prm.counters[4], s_lane2);
+#if FB_PHASES
+        ph[10] = clock64() - phLast;
+        for (int k = 0; k < 12; k++) atomicAdd(&prm.counters[8 + k], (unsigned long long)ph[k]);
+        atomicAdd(&prm.counters[20], (unsigned long long)calls);
+#endif
     }
 }
 
@@ -1031,7 +1069,7 @@ extern "C" fb_status fb_ctx_create(int32_t device, fb_ctx** out) {
     CK(cudaFuncSetAttribute(fb_em_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     CK(cudaFuncSetAttribute(fb_em_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     for (int b = 0; b <= kNumBuckets; b++) { CK(cudaStreamCreateWithFlags(&c->bstream[b], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->bev[b], cudaEventDisableTiming)); }
-    CK(c->d_ctr.ensure(8)); CK(cudaMemset(c->d_ctr.p, 0, 8 * sizeof(unsigned long long)));
+    CK(c->d_ctr.ensure(32)); CK(cudaMemset(c->d_ctr.p, 0, 32 * sizeof(unsigned long long)));
     if (device < 64) {
         DevClock& k = g_clock[device]; std::lock_guard<std::mutex> l(k.mu);
         if (!k.epoch) { CK(cudaEventCreate(&k.epoch)); CK(cudaEventRecord(k.epoch, c->stream)); CK(cudaEventSynchronize(k.epoch)); }
@@ -1274,7 +1312,7 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
     }
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaMemcpyAsync(c->h_out, c->d_out.p, outTotal, cudaMemcpyDeviceToHost, c->stream));
-    unsigned long long hc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long hc[32] = {0};
     CK(cudaMemcpyAsync(hc, c->d_ctr.p, sizeof hc, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
@@ -1290,6 +1328,15 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
     }
     c->ctr.placements_p1 = (int64_t)hc[0]; c->ctr.placements_p2 = (int64_t)hc[1]; c->ctr.base_terms = (int64_t)hc[2];
     c->ctr.lane_steps_p1 = (int64_t)hc[3]; c->ctr.lane_steps_p2 = (int64_t)hc[4];
+#if FB_PHASES
+    if (getenv("FIGBIRD_PHASES")) {
+        static const char* nm[12] = {"prologue", "walk", "finish1", "gather", "combine", "consensus", "prephase", "pass2", "finish2", "endsweep", "epilogue", "-"};
+        double tot = 0; for (int k = 0; k < 11; k++) tot += (double)hc[8 + k];
+        fprintf(stderr, "phases (cumulative, %llu rounds):", hc[20]);
+        for (int k = 0; k < 11; k++) fprintf(stderr, " %s %.1f%%", nm[k], 100.0 * hc[8 + k] / (tot > 0 ? tot : 1));
+        fprintf(stderr, " | cycles/round %.0f\n", tot / (hc[20] ? hc[20] : 1));
+    }
+#endif
     for (int i = 0; i < n; i++) {
         FbItemOut* H = (FbItemOut*)(c->h_out + di[i].out_off);
         const DevGap& g = c->hGaps[items[i].gap];
