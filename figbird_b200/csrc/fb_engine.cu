@@ -181,6 +181,9 @@ __device__ __forceinline__ void band(const DevModel& m, const DevGap& g, int fl,
 
 // Pass-1 weight rows are stored in four planes by (placement index mod 4): the gather's lanes own 4 consecutive gap rows each,
 // so at any read base they need indices 4*lane + const -- one plane, consecutive entries, no bank conflicts.
+#ifndef FB_FIN
+#define FB_FIN 1      // placements per lane and trip in the finish phase (independent log / exp chains)
+#endif
 #ifndef FB_WTR
 #define FB_WTR 0
 #endif
@@ -207,13 +210,13 @@ __device__ __forceinline__ double placementWeight(double p, bool unm) {
     // and let one IEEE multiply do the final scaling.
     double s = log(p);
     const bool tiny = s < -290.0;
-    if (tiny) s += 300.0;
+    s = tiny ? s + 300.0 : s;
     const double LN10_HI = 2.302585092994045901e+00, LN10_LO = -2.170756223382249351e-16;
     const double ph = __dmul_rn(s, LN10_HI);
     const double pl = __fma_rn(s, LN10_HI, -ph) + s * LN10_LO;
     double w = exp(ph);
     w = __fma_rn(w, pl, w);
-    return tiny ? __dmul_rn(w, 1e-300) : w;
+    return __dmul_rn(w, tiny ? 1e-300 : 1.0);      // (x * 1.0 is exact: one code path, no divergence)
 }
 
 // ---- flank products, once per gap batch.  One block per read.
@@ -696,21 +699,37 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                     const double* LF = prm.lfrf + 2 * prm.read_off[qi];
                     const double* RF = LF + len;
                     double best = 0.0; int bestI = 0x7fffffff;
-                    for (int i = lane; i < n; i += 32) {
-                        const int x0 = xlo + i;
-                        double p = 1.0;
-                        if (unm) {
-                            const long long t = (fl & FB_READ_LEFT) ? ((long long)x0 - rel + len) : ((long long)rel + offLg + len - x0);
-                            p = m.pdf[min(max((int)t, 0), m.n_insert - 1)];
+                    // FB_FIN placements per lane and trip: the log / exp chains of the weight are long and independent
+                    for (int i0 = lane; i0 < n; i0 += 32 * FB_FIN) {
+                        double p[FB_FIN], w[FB_FIN];
+#pragma unroll
+                        for (int u = 0; u < FB_FIN; u++) {
+                            const int i = i0 + 32 * u;
+                            p[u] = 0.0;
+                            if (i < n) {
+                                const int x0 = xlo + i;
+                                double v = 1.0;
+                                if (unm) {
+                                    const long long t = (fl & FB_READ_LEFT) ? ((long long)x0 - rel + len) : ((long long)rel + offLg + len - x0);
+                                    v = m.pdf[min(max((int)t, 0), m.n_insert - 1)];
+                                }
+                                if (x0 < 0) v = __dmul_rn(v, LF[-x0]);
+                                if (min(jhi, Lg - x0) > max(jlo, -x0)) v = __dmul_rn(v, Wq[wtr(i, np)]);
+                                const int b = x0 + len - Lg;
+                                if (b > 0) v = __dmul_rn(v, RF[b]);
+                                p[u] = (v > 0.0) ? v : 0.0;
+                            }
                         }
-                        if (x0 < 0) p = __dmul_rn(p, LF[-x0]);
-                        if (min(jhi, Lg - x0) > max(jlo, -x0)) p = __dmul_rn(p, Wq[wtr(i, np)]);
-                        const int b = x0 + len - Lg;
-                        if (b > 0) p = __dmul_rn(p, RF[b]);
-                        double w = 0.0;
-                        if (p > 0.0) w = placementWeight(p, unm); else p = 0.0;
-                        Wq[wtr(i, np)] = w;
-                        if (p > best) { best = p; bestI = i; }
+#pragma unroll
+                        for (int u = 0; u < FB_FIN; u++) w[u] = placementWeight(p[u] > 0.0 ? p[u] : 1.0, unm);
+#pragma unroll
+                        for (int u = 0; u < FB_FIN; u++) {
+                            const int i = i0 + 32 * u;
+                            if (i < n) {
+                                Wq[wtr(i, np)] = (p[u] > 0.0) ? w[u] : 0.0;
+                                if (p[u] > best) { best = p[u]; bestI = i; }
+                            }
+                        }
                     }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
