@@ -58,13 +58,16 @@ void bumpInsert(Stats& s, int index) {   // Figbird.cpp:186-225
     s.maxInsertSize = grown;
 }
 
+// strncpy without the zero fill of the whole buffer (these run four times per SAM line)
+static inline void copyBounded(char* dst, const char* src, size_t cap) { size_t n = strnlen(src, cap - 1); memcpy(dst, src, n); dst[n] = 0; }
+
 // One CIGAR walk shared by the two passes.  `delims` is what strtok splits on (the two reference
 // functions differ: "IDMS^\t\n " vs "IDM^\t\n ").  The op letter is looked up in the ORIGINAL string at the
 // running offset, exactly as the reference does (Figbird.cpp:325-375, 988-1039).
 template <class OnOp>
 void walkCigar(const char* cigar, const char* delims, OnOp onOp) {
     char buf[1024];
-    strncpy(buf, cigar, sizeof buf - 1); buf[sizeof buf - 1] = 0;
+    copyBounded(buf, cigar, sizeof buf);
     Tokens tk(buf);
     int consumed = 0;
     const size_t clen = strlen(cigar);
@@ -81,7 +84,7 @@ void walkCigar(const char* cigar, const char* delims, OnOp onOp) {
 template <class OnMis>
 void walkMD(const char* md, const std::vector<int>& inserts, OnMis onMis) {
     char buf[1024];
-    strncpy(buf, md, sizeof buf - 1); buf[sizeof buf - 1] = 0;
+    copyBounded(buf, md, sizeof buf);
     const unsigned long mdLength = strlen(md) - 5;
     Tokens tk(buf);
     tk.next(":"); tk.next(":");
@@ -123,7 +126,7 @@ bool splitMyout(char* line, SamFields& f, char* mdKeep /*persisting MD buffer*/)
     f.tlen = atoi(t);
     f.haveMd = f.haveNh = false;
     while ((t = tk.next("\t\n")) != nullptr) {
-        if (t[0] == 'M' && t[1] == 'D') { strncpy(mdKeep, t, 999); mdKeep[999] = 0; f.haveMd = true; }
+        if (t[0] == 'M' && t[1] == 'D') { copyBounded(mdKeep, t, 1000); f.haveMd = true; }
         else if (t[0] == 'I' && t[1] == 'H') { f.nh = atoi(t + 5); f.haveNh = true; }
     }
     return true;
