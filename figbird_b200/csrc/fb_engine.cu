@@ -104,6 +104,7 @@ struct Params {
     double* lfrf;                   // per read: LF[len] then RF[len] at 2*read_off (fb_flank_kernel)
     const DevItem* items;
     const unsigned char* in_arena; unsigned char* out_arena; unsigned char* scratch; unsigned char* meta;
+    double e_tab[512];              // e[k] at [k], e[max_read_len-1-i] at [256+i]: read with a warp-uniform index through the constant bank (LDC)
     unsigned long long* counters;   // [0] pass-1 placements, [1] pass-2 placements, [2] base terms, [3] pass-1 lane steps, [4] pass-2 lane steps
 };
 
@@ -770,7 +771,11 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                     int jw = (m0 + 1) * Lg - xm;       // read base at which the walk re-enters gap row 0 (> js)
                     const double2* ptr = UT + xm;      // + j: cyclically extended table, plane 0
                     const unsigned short* rc = RC2 + ql * mlp;
-                    const double* me = ((r.packed >> 24) & FB_READ_REVERSE) ? MER + (m.max_read_len - len) : ME;     // me[j] = e of read base j
+                    // me[j] = e of read base j: kernel-parameter (constant bank) table, or shared memory when reads are longer than it
+                    const bool revRead = (r.packed >> 24) & FB_READ_REVERSE;
+                    const int eBase = revRead ? 256 + (m.max_read_len - len) : 0;
+                    struct ETab { const Params& p; int base; __device__ __forceinline__ double operator[](int j) const { return p.e_tab[base + j]; } };
+                    const ETab me{prm, eBase};
                     double acc = 1.0, save = 1.0;
                     const bool oneWrap = (je - js) <= Lg;     // a lane re-enters row 0 at most once: keep the first product in a register
                     auto mul = [&](const double2 v, double e) { acc = __dmul_rn(acc, __fma_rn(e, v.y, v.x)); };
@@ -1061,6 +1066,7 @@ struct fb_ctx {
     unsigned char* h_out = nullptr; size_t h_out_cap = 0;     // pinned result arena
     unsigned char* h_in = nullptr; size_t h_in_cap = 0;       // pinned staging for items + inputs
     FbCounters ctr{};
+    double hEtab[512] = {};        // host copy of Params::e_tab
 };
 
 // Kernel intervals of all contexts on one physical device, on one time base (an epoch event per device): contexts that
@@ -1154,6 +1160,8 @@ extern "C" fb_status fb_model_upload(fb_ctx* c, const FbModel* m) {
         }
         if (m->prob_cutoff <= 0) c->dm.accept_min_p = INFINITY;   // -log10(p) < 0 needs p > 1: never for a probability
     }
+    if (RL > 256) { c->err = "reads longer than 256 bases are not supported by this build"; return FB_ERR_ARG; }
+    for (int k = 0; k < RL; k++) { c->hEtab[k] = m->err_pos[k]; c->hEtab[256 + (RL - 1 - k)] = m->err_pos[k]; }
     c->haveModel = true; c->flankDirty = true;
     return FB_OK;
 }
@@ -1310,6 +1318,7 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
     prm.flank = c->d_flank.p; prm.pile_l = c->d_pl.p; prm.pile_r = c->d_pr.p; prm.read_gap = c->d_rgap.p; prm.lfrf = c->d_lfrf.p; prm.meta = c->d_meta.p;
     prm.items = (const DevItem*)c->d_in.p; prm.in_arena = c->d_in.p + itemsBytes; prm.out_arena = c->d_out.p; prm.scratch = c->d_scratch.p;
     prm.counters = c->d_ctr.p;
+    memcpy(prm.e_tab, c->hEtab, sizeof prm.e_tab);
 
     int launches = 0;
     if (c->flankDirty) {      // flank products of every read of the batch, once (model and batch are both resident now)
