@@ -1040,7 +1040,7 @@ __global__ void __launch_bounds__(256) fb_fp64_peak_kernel(double* out, int iter
 
 template <class T> struct DevBuf {
     T* p = nullptr; size_t cap = 0;
-    cudaError_t ensure(size_t n) { if (n <= cap) return cudaSuccess; if (p) cudaFree(p); p = nullptr; cap = 0; size_t want = n + n / 4 + 64; cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T)); if (e == cudaSuccess) cap = want; return e; }
+    cudaError_t ensure(size_t n) { if (n <= cap) return cudaSuccess; if (p) cudaFree(p); p = nullptr; cap = 0; size_t want = n + n / 2 + 64; cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T)); if (e == cudaSuccess) cap = want; return e; }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
@@ -1295,7 +1295,7 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
     const size_t itemsBytes = al(sizeof(DevItem) * (size_t)n);
     const size_t orderOff = itemsBytes + al(inTotal);
     const size_t inBytes = orderOff + al(sizeof(int) * (size_t)n) + 16;
-    if (inBytes > c->h_in_cap) { if (c->h_in) cudaFreeHost(c->h_in); c->h_in = nullptr; c->h_in_cap = 0; size_t want = inBytes + inBytes / 2; CK(cudaMallocHost((void**)&c->h_in, want)); c->h_in_cap = want; }
+    if (inBytes > c->h_in_cap) { if (c->h_in) cudaFreeHost(c->h_in); c->h_in = nullptr; c->h_in_cap = 0; size_t want = 2 * inBytes; CK(cudaMallocHost((void**)&c->h_in, want)); c->h_in_cap = want; }
     memcpy(c->h_in, di.data(), sizeof(DevItem) * (size_t)n);
     memcpy(c->h_in + orderOff, order.data(), sizeof(int) * (size_t)n);
     for (int i = 0; i < n; i++) {
@@ -1307,7 +1307,7 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
     CK(c->d_out.ensure(outTotal + 16));
     CK(c->d_scratch.ensure(scratchTotal + 16));
     CK(c->d_meta.ensure(metaTotal + 16));
-    if (outTotal + 16 > c->h_out_cap) { if (c->h_out) cudaFreeHost(c->h_out); c->h_out = nullptr; c->h_out_cap = 0; size_t want = outTotal + outTotal / 2 + 64; CK(cudaMallocHost((void**)&c->h_out, want)); c->h_out_cap = want; }
+    if (outTotal + 16 > c->h_out_cap) { if (c->h_out) cudaFreeHost(c->h_out); c->h_out = nullptr; c->h_out_cap = 0; size_t want = 2 * outTotal + 64; CK(cudaMallocHost((void**)&c->h_out, want)); c->h_out_cap = want; }
     CK(cudaMemcpyAsync(c->d_in.p, c->h_in, inBytes, cudaMemcpyHostToDevice, c->stream));
     c->ctr.h2d_bytes += (int64_t)inBytes;
 

@@ -121,12 +121,13 @@ static void parallelFor(int n, int threads, F f) {
 
 // Engine contexts survive fb_fillgaps_main: an in-process caller (one FillGaps call per pipeline iteration) pays stream /
 // buffer / pinned-arena creation once per (device, lane).  Leaked on purpose at process exit.
-struct CtxPool { std::mutex mu; std::vector<std::pair<int, fb_ctx*>> idle; };
+struct CtxPool { std::mutex mu; std::vector<std::pair<long, fb_ctx*>> idle; };      // key = device * 1024 + lane: a lane gets its own context back (arenas already sized for its shard)
 static CtxPool& ctxPool() { static CtxPool* p = new CtxPool; return *p; }
-static fb_ctx* acquireCtx(int device, std::string& err) {
+static fb_ctx* acquireCtx(int device, int lane, std::string& err) {
     {
         CtxPool& P = ctxPool(); std::lock_guard<std::mutex> l(P.mu);
-        for (size_t i = 0; i < P.idle.size(); i++) if (P.idle[i].first == device) { fb_ctx* c = P.idle[i].second; P.idle.erase(P.idle.begin() + i); return c; }
+        const long key = (long)device * 1024 + lane;
+        for (size_t i = 0; i < P.idle.size(); i++) if (P.idle[i].first == key) { fb_ctx* c = P.idle[i].second; P.idle.erase(P.idle.begin() + i); return c; }
     }
     fb_ctx* ctx = nullptr;
     if (fb_ctx_create(device, &ctx) != FB_OK || !ctx) {
@@ -136,7 +137,7 @@ static fb_ctx* acquireCtx(int device, std::string& err) {
     }
     return ctx;
 }
-static void releaseCtx(int device, fb_ctx* ctx) { CtxPool& P = ctxPool(); std::lock_guard<std::mutex> l(P.mu); P.idle.emplace_back(device, ctx); }
+static void releaseCtx(int device, int lane, fb_ctx* ctx) { CtxPool& P = ctxPool(); std::lock_guard<std::mutex> l(P.mu); P.idle.emplace_back((long)device * 1024 + lane, ctx); }
 
 static std::vector<int> visibleDevices() {
     std::vector<int> d;
@@ -232,7 +233,8 @@ int fillgapsMain(int argc, const char* const* argv) {
         const std::vector<int>& mine = shard[d];
         if (mine.empty()) return;
         auto d0 = clk::now();
-        fb_ctx* ctx = acquireCtx(devs[d], devErr[d]);
+        int laneOf = 0; for (int e2 = 0; e2 < d; e2++) if (devs[e2] == devs[d]) laneOf++;
+        fb_ctx* ctx = acquireCtx(devs[d], laneOf, devErr[d]);
         if (!ctx) return;
         FbCounters ctr0{}; fb_get_counters(ctx, &ctr0);
         // batch of this shard
@@ -261,7 +263,7 @@ int fillgapsMain(int argc, const char* const* argv) {
         B.read_flags = rfl.data(); B.read_jlo = rjlo.data(); B.read_jcut = rjcut.data(); B.n_codes = (int64_t)codes.size(); B.read_codes = codes.data();
         B.n_flank = (int64_t)flank.size(); B.flank_codes = flank.data(); B.n_pile_rows = (int64_t)(pileL.size() / 4); B.pile_left = pileL.data(); B.pile_right = pileR.data();
         if (fb_batch_upload(ctx, &B) != FB_OK) { devErr[d] = std::string("fb_batch_upload: ") + fb_last_error(ctx); fb_ctx_destroy(ctx); return; }
-        if (!waitModel()) { releaseCtx(devs[d], ctx); return; }      // reported by the main thread
+        if (!waitModel()) { releaseCtx(devs[d], laneOf, ctx); return; }      // reported by the main thread
         FbModel fm{};
         fm.max_read_len = model.maxReadLength; fm.err_pos = model.errorPosDist.data(); fm.ins_pos = model.inPosDist.data(); fm.del_pos = model.delPosDist.data();
         for (int i = 0; i < 5; i++) for (int j = 0; j < 5; j++) fm.err_type[i * 5 + j] = model.errorTypeProbs[i][j];
@@ -296,7 +298,7 @@ int fillgapsMain(int argc, const char* const* argv) {
             devCtr[d] = c1;
         }
         devTicks[d] = q.ticks(); devEng[d] = q.engineSeconds(); devCopy[d] = q.copySeconds();
-        releaseCtx(devs[d], ctx);
+        releaseCtx(devs[d], laneOf, ctx);
     });
     for (auto& t : devThreads) t.join();
     if (!waitModel()) { printf("%s\n", err.c_str()); return 1; }

@@ -1082,7 +1082,10 @@ GapResult GapFill::run(DeviceQueue& dev, int batchGapIndex) {
 
     // speculative evaluation: candidates are scored in chunks on the device, then the reference's
     // sequential scan is replayed over the results; work past an early exit is discarded.
-    const int chunk = largeGapFlag_ ? 1 : (partialFlag ? 16 : 24);
+    // candidates per device request: more means fewer engine calls (ticks) but more work past an early exit
+    static const int chunkP = [] { const char* e = getenv("FIGBIRD_CHUNK_PARTIAL"); return e ? std::max(1, atoi(e)) : 16; }();
+    static const int chunkU = [] { const char* e = getenv("FIGBIRD_CHUNK_UNMAPPED"); return e ? std::max(1, atoi(e)) : 24; }();
+    const int chunk = largeGapFlag_ ? 1 : (partialFlag ? chunkP : chunkU);
     std::vector<ItemResult> chunkRes; int chunkBase = 0;
     bool broke = false;
     for (; j < range; j++) {
