@@ -159,3 +159,39 @@ def test_partial_subnormal_weights():
         assert not [m for m in synth.compare_results(x, y, cutoff=model["prob_cutoff"]) if not m.startswith("counts")]
         m = (x["counts"] > 0) & (x["counts"] < 2.3e-308)
         assert np.array_equal(x["counts"][m], y["counts"][m]), "subnormal weights must match bit for bit"
+
+
+def test_many_reads_take_the_chunked_path():
+    """Read sets whose weight rows do not fit the chunk region at once (the cap of the reference is 3000 reads per gap,
+    Figbird.cpp:114-115): reads are staged and gathered chunk by chunk; results must not depend on the chunking."""
+    rng = np.random.default_rng(31)
+    model_u = synth.make_model(seed=31)
+    gaps = [synth.make_gap(rng, capi.FB_MODE_UNMAPPED, 120, 110, n_reads=700),
+            synth.make_gap(rng, capi.FB_MODE_UNMAPPED, 40, 44, n_reads=3000)]
+    items = [dict(gap=0, cand_len=120, max_rounds=3, flags=capi.FB_FLAG_WANT_COUNTS | capi.FB_FLAG_NO_COMP_STOP),
+             dict(gap=0, cand_len=33, max_rounds=2, flags=capi.FB_FLAG_WANT_COUNTS | capi.FB_FLAG_NO_COMP_STOP | capi.FB_FLAG_EXTRA_PASS),
+             dict(gap=1, cand_len=40, max_rounds=2, flags=capi.FB_FLAG_WANT_COUNTS | capi.FB_FLAG_NO_COMP_STOP)]
+    a, b = _run_both(model_u, gaps, items)
+    _assert_same(a, b, items, model_u)
+    model_p = synth.make_model(seed=32, partial=True)
+    gaps = [synth.make_gap(rng, capi.FB_MODE_PARTIAL, 90, 80, n_reads=900)]
+    fl = capi.FB_FLAG_RECORD_ALL | capi.FB_FLAG_NO_COMP_STOP | capi.FB_FLAG_WANT_COUNTS
+    items = [dict(gap=0, cand_len=L, max_rounds=3, flags=fl) for L in (0, 60, 90, 250)]
+    a, b = _run_both(model_p, gaps, items)
+    _assert_same(a, b, items, model_p)
+
+
+def test_empty_and_short_inputs():
+    """A gap without reads, reads much shorter than the model's read length, and candidate lengths around the read length."""
+    rng = np.random.default_rng(33)
+    model = synth.make_model(seed=33)
+    g_empty = synth.make_gap(rng, capi.FB_MODE_UNMAPPED, 30, 30, n_reads=0)
+    g_short = synth.make_gap(rng, capi.FB_MODE_UNMAPPED, 50, 45, L=36, n_reads=40)
+    g_edge = synth.make_gap(rng, capi.FB_MODE_UNMAPPED, 100, 100, n_reads=30)
+    gaps = [g_empty, g_short, g_edge]
+    items = [dict(gap=0, cand_len=L, max_rounds=3, flags=capi.FB_FLAG_WANT_COUNTS) for L in (0, 30)]
+    items += [dict(gap=1, cand_len=L, max_rounds=200, flags=capi.FB_FLAG_WANT_COUNTS | capi.FB_FLAG_EXTRA_PASS) for L in (1, 35, 36, 37, 50, 140)]
+    items += [dict(gap=2, cand_len=L, max_rounds=200, flags=capi.FB_FLAG_WANT_COUNTS) for L in (31, 32, 33, 63, 64, 65, 99, 100, 101, 127, 128, 129)]
+    items += [dict(kind=capi.FB_ITEM_HARD, gap=0, cand_len=30, string_in=rng.integers(0, 4, 30).astype(np.uint8))]
+    a, b = _run_both(model, gaps, items)
+    _assert_same(a, b, items, model)
