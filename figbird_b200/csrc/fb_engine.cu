@@ -74,7 +74,7 @@ constexpr int kChunkWant = 72 * 1024;     // weights + read-code staging we ask 
 constexpr int kNumBuckets = 4;
 __host__ __device__ constexpr int bucketCap(int b) { return b == 0 ? 36 * 1024 : b == 1 ? 72 * 1024 : b == 2 ? 112 * 1024 : kMaxSmem; }
 
-struct DevGap { long long gap_start; int mode, orig_len, n_reads, read_begin, flank_len, flank_begin, pile_len, pile_begin; };
+struct DevGap { long long gap_start; int mode, orig_len, n_reads, read_begin, flank_len, flank_begin, pile_len, pile_begin, flank_pk, pad_; };   // flank_pk: first packed word of the left flank
 
 struct DevItem {
     int kind, gap, Lg, max_rounds, flags, comp_in;
@@ -99,8 +99,10 @@ struct Params {
     DevModel m;
     const DevGap* gaps;
     const int* read_len; const long long* read_off; const int* read_mate; const int* read_gap;
-    const unsigned char* read_flags; const unsigned char* read_jlo; const unsigned char* read_jcut; const unsigned char* codes;
-    const unsigned char* flank; const int* pile_l; const int* pile_r;
+    const unsigned char* read_flags; const unsigned char* read_jlo; const unsigned char* read_jcut;
+    // reads and flanks in HBM: 2 bits per base + an N mask, 16 bases per uint2 {codes, mask}; every read / flank starts a word
+    const uint2* codes_pk; const long long* read_pk_off; const uint2* flank_pk;
+    const int* pile_l; const int* pile_r;
     double* lfrf;                   // per read: LF[len] then RF[len] at 2*read_off (fb_flank_kernel)
     const DevItem* items;
     const unsigned char* in_arena; unsigned char* out_arena; unsigned char* scratch; unsigned char* meta;
@@ -190,6 +192,9 @@ __device__ __forceinline__ void band(const DevModel& m, const DevGap& g, int fl,
 #endif
 __device__ __forceinline__ int wtr(int i, int np) { return FB_WTR ? (i & 3) * np + (i >> 2) : i; }
 
+// base code i of a packed sequence (A0 C1 G2 T3, 4 = N / other)
+__device__ __forceinline__ int pkCode(const uint2* p, int i) { const uint2 w = p[i >> 4]; const int sft = i & 15; return ((w.y >> sft) & 1u) ? 4 : (int)((w.x >> (2 * sft)) & 3u); }
+
 // E[j] = sum_{k<4, k!=j} P[k]*ETP[k][j] in k order (Figbird.cpp:2118-2137)
 __device__ __forceinline__ void errRow(const double* etp, const double p[4], double e[5]) {
 #pragma unroll
@@ -245,9 +250,9 @@ __global__ void __launch_bounds__(128) fb_flank_kernel(const Params prm, int nRe
     const int len = prm.read_len[q], fl = prm.read_flags[q];
     const int jlo = prm.read_jlo[q], jhi = len - prm.read_jcut[q];
     const int F = g.flank_len;
-    const unsigned char* rc = prm.codes + prm.read_off[q];
-    const unsigned char* lf = prm.flank + g.flank_begin;
-    const unsigned char* rf = lf + F;
+    const uint2* rc = prm.codes_pk + prm.read_pk_off[q];
+    const uint2* lf = prm.flank_pk + g.flank_pk;
+    const uint2* rf = lf + ((F + 15) >> 4);
     const bool rev = fl & FB_READ_REVERSE;
     double* LF = prm.lfrf + 2 * prm.read_off[q];
     double* RF = LF + len;
@@ -255,12 +260,12 @@ __global__ void __launch_bounds__(128) fb_flank_kernel(const Params prm, int nRe
         double pl = 1.0, pr = 1.0;
         const int je = jhi < a ? jhi : a;
         for (int j = jlo; j < je; j++) {
-            const int f = lf[F - a + j], c = rc[j];
+            const int f = pkCode(lf, F - a + j), c = pkCode(rc, j);
             pl *= __fma_rn(prm.m.e[rev ? (len - 1 - j) : j], sD[f * 5 + c], sP[f * 5 + c]);
         }
         const int js = jlo > len - a ? jlo : len - a;
         for (int j = js; j < jhi; j++) {
-            const int f = rf[j - (len - a)], c = rc[j];
+            const int f = pkCode(rf, j - (len - a)), c = pkCode(rc, j);
             pr *= __fma_rn(prm.m.e[rev ? (len - 1 - j) : j], sD[f * 5 + c], sP[f * 5 + c]);
         }
         LF[a] = pl; RF[a] = pr;
@@ -312,8 +317,8 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
     unsigned char* oHard = out + it.off_hard;
     int* oCov = (int*)(out + it.off_cov);
 
-    const unsigned char* lf = prm.flank + g.flank_begin;
-    const unsigned char* rf = lf + F;
+    const uint2* lf = prm.flank_pk + g.flank_pk;
+    const uint2* rf = lf + ((F + 15) >> 4);
 
     if (tid == 0) { s_same[0] = 1; s_same[1] = 1; s_gchg = 0; s_next1 = 0; s_next2 = 0; s_flags = 0; s_lane1 = 0; s_lane2 = 0; s_terms = 0; s_nsum = 0; }
     int comp = 0;          // comp_count (Figbird.cpp:3919-3927), kept identically by every thread
@@ -323,7 +328,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
     if (tid < 25) ETP[tid] = m.etp[tid];
     for (int r = tid; r < rows; r += kThreads) {
         const int x = r - F;
-        if (x < 0 || x >= Lg) G[r] = (r < F) ? lf[r] : rf[r - F - Lg];     // gap part is written by the consensus / string_in
+        if (x < 0 || x >= Lg) G[r] = (unsigned char)((r < F) ? pkCode(lf, r) : pkCode(rf, r - F - Lg));     // gap part is written by the consensus / string_in
     }
     __syncthreads();
     // ---- per-read admissible band, prefix sums of band widths (W rows) and of pass-1 / pass-2 work units
@@ -435,12 +440,26 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
             RM[ql] = r;
             if (ql < nq) { CNT[ql] = 0; CNT[nq + ql] = 0; X1P[ql] = INT_MIN; THR[ql] = 0.0; }
         }
-        const int n = nq * mlp;
-        for (int i = tid; i < n; i += kThreads) {
-            const int ql = i / mlp, j = i - ql * mlp;
+        // one packed word (16 bases: 8-byte load, consecutive threads -> consecutive words) per thread and trip
+        const int wpr = mlp >> 4, nw = nq * wpr;
+        const unsigned s8 = (unsigned)(S >> 3);
+        for (int i = tid; i < nw; i += kThreads) {
+            const int ql = i / wpr, wj = i - ql * wpr;
             const int qi = g.read_begin + q0 + ql;
-            const unsigned char c = (j < prm.read_len[qi]) ? prm.codes[prm.read_off[qi] + j] : (unsigned char)4;
-            RC[i] = c; RC2[i] = (unsigned short)(c * (S >> 3));
+            const int len = prm.read_len[qi];
+            uint2 w = make_uint2(0u, 0xffffu);
+            if (16 * wj < len) w = prm.codes_pk[prm.read_pk_off[qi] + wj];
+            unsigned cb[4] = {0, 0, 0, 0}, co[8];
+#pragma unroll
+            for (int t = 0; t < 16; t++) {
+                const unsigned c = (16 * wj + t >= len || ((w.y >> t) & 1u)) ? 4u : ((w.x >> (2 * t)) & 3u);
+                cb[t >> 2] |= c << (8 * (t & 3));
+                if (t & 1) co[t >> 1] |= (c * s8) << 16; else co[t >> 1] = c * s8;
+            }
+            uint4* rcp = (uint4*)(RC + (size_t)ql * mlp + 16 * wj);
+            *rcp = make_uint4(cb[0], cb[1], cb[2], cb[3]);
+            uint4* r2p = (uint4*)(RC2 + (size_t)ql * mlp + 16 * wj);
+            r2p[0] = make_uint4(co[0], co[1], co[2], co[3]); r2p[1] = make_uint4(co[4], co[5], co[6], co[7]);
         }
     };
     // reads [q0, q1) whose records + codes + weight rows fit the chunk region (at least one read)
@@ -1059,7 +1078,8 @@ struct fb_ctx {
     DevBuf<double> d_e, d_match, d_pdf, d_lfrf;
     std::vector<DevGap> hGaps; std::vector<int> hGapMaxLen;
     DevBuf<DevGap> d_gaps; DevBuf<int> d_rlen, d_rmate, d_rgap, d_pl, d_pr; DevBuf<long long> d_roff;
-    DevBuf<unsigned char> d_rfl, d_jlo, d_jcut, d_codes, d_flank;
+    DevBuf<unsigned char> d_rfl, d_jlo, d_jcut;
+    DevBuf<uint2> d_codes_pk, d_flank_pk; DevBuf<long long> d_pkoff;
     DevBuf<DevItem> d_items; DevBuf<unsigned char> d_in, d_out, d_scratch, d_meta;
     int nReads = 0; bool flankDirty = true;        // LF/RF products must be (re)computed before the next fb_em_run
     DevBuf<unsigned long long> d_ctr;
@@ -1108,7 +1128,7 @@ extern "C" void fb_ctx_destroy(fb_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->d_e.release(); c->d_match.release(); c->d_pdf.release(); c->d_lfrf.release(); c->d_rgap.release(); c->d_meta.release();
     c->d_gaps.release(); c->d_rlen.release(); c->d_rmate.release(); c->d_pl.release(); c->d_pr.release(); c->d_roff.release();
-    c->d_rfl.release(); c->d_jlo.release(); c->d_jcut.release(); c->d_codes.release(); c->d_flank.release();
+    c->d_rfl.release(); c->d_jlo.release(); c->d_jcut.release(); c->d_codes_pk.release(); c->d_flank_pk.release(); c->d_pkoff.release();
     c->d_items.release(); c->d_in.release(); c->d_out.release(); c->d_scratch.release(); c->d_ctr.release();
     if (c->h_out) cudaFreeHost(c->h_out);
     if (c->h_in) cudaFreeHost(c->h_in);
@@ -1189,7 +1209,6 @@ extern "C" fb_status fb_batch_upload(fb_ctx* c, const FbGapBatch* b) {
         c->hGapMaxLen[i] = ml;
     }
     fb_status s;
-    if ((s = upload(c, c->d_gaps, c->hGaps.data(), c->hGaps.size()))) return s;
     if ((s = upload(c, c->d_rlen, b->read_len, (size_t)b->n_reads))) return s;
     if ((s = upload(c, c->d_rmate, b->read_mate, (size_t)b->n_reads))) return s;
     if ((s = upload(c, c->d_rgap, readGap.data(), (size_t)b->n_reads))) return s;
@@ -1199,8 +1218,41 @@ extern "C" fb_status fb_batch_upload(fb_ctx* c, const FbGapBatch* b) {
     if ((s = upload(c, c->d_rfl, b->read_flags, (size_t)b->n_reads))) return s;
     if ((s = upload(c, c->d_jlo, b->read_jlo, (size_t)b->n_reads))) return s;
     if ((s = upload(c, c->d_jcut, b->read_jcut, (size_t)b->n_reads))) return s;
-    if ((s = upload(c, c->d_codes, b->read_codes, (size_t)b->n_codes))) return s;
-    if ((s = upload(c, c->d_flank, b->flank_codes, (size_t)b->n_flank))) return s;
+    {   // reads and flanks go to the device 2-bit packed with an N mask (16 bases per 8-byte word, each sequence word-aligned)
+        auto pack = [](const uint8_t* src, int n, std::vector<uint2>& dst) {
+            for (int w = 0; w < (n + 15) / 16; w++) {
+                uint2 v = make_uint2(0u, 0u);
+                for (int t = 0; t < 16 && 16 * w + t < n; t++) {
+                    const unsigned cde = src[16 * w + t];
+                    if (cde < 4) v.x |= cde << (2 * t); else v.y |= 1u << t;
+                }
+                dst.push_back(v);
+            }
+        };
+        std::vector<uint2> pk; std::vector<long long> pkoff((size_t)std::max(b->n_reads, 1), 0);
+        pk.reserve((size_t)b->n_codes / 16 + (size_t)b->n_reads + 1);
+        for (int q = 0; q < b->n_reads; q++) {
+            pkoff[q] = (long long)pk.size();
+            const long long o = b->read_code_off[q]; const int len = b->read_len[q];
+            if (o >= 0 && len > 0 && o + len <= b->n_codes) pack(b->read_codes + o, len, pk);
+        }
+        if (pk.empty()) pk.push_back(make_uint2(0u, 0xffffu));
+        std::vector<uint2> fpk;
+        for (int i = 0; i < b->n_gaps; i++) {
+            const FbGap& g = b->gaps[i];
+            c->hGaps[i].flank_pk = (int)fpk.size();
+            if (g.flank_len > 0 && g.flank_begin >= 0 && (long long)g.flank_begin + 2LL * g.flank_len <= b->n_flank) {
+                pack(b->flank_codes + g.flank_begin, g.flank_len, fpk);
+                pack(b->flank_codes + g.flank_begin + g.flank_len, g.flank_len, fpk);
+            } else if (g.flank_len > 0) { c->err = "flank codes out of range"; return FB_ERR_ARG; }
+        }
+        if (fpk.empty()) fpk.push_back(make_uint2(0u, 0xffffu));
+        if ((s = upload(c, c->d_gaps, c->hGaps.data(), c->hGaps.size()))) return s;      // (after flank_pk is known)
+        if ((s = upload(c, c->d_codes_pk, pk.data(), pk.size()))) return s;
+        if ((s = upload(c, c->d_pkoff, pkoff.data(), pkoff.size()))) return s;
+        if ((s = upload(c, c->d_flank_pk, fpk.data(), fpk.size()))) return s;
+        CK(cudaStreamSynchronize(c->stream));
+    }
     if ((s = upload(c, c->d_pl, b->pile_left, (size_t)b->n_pile_rows * 4))) return s;
     if ((s = upload(c, c->d_pr, b->pile_right, (size_t)b->n_pile_rows * 4))) return s;
     CK(cudaStreamSynchronize(c->stream));
@@ -1314,8 +1366,9 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
     Params prm{};
     prm.m = c->dm;
     prm.gaps = c->d_gaps.p; prm.read_len = c->d_rlen.p; prm.read_off = c->d_roff.p; prm.read_mate = c->d_rmate.p;
-    prm.read_flags = c->d_rfl.p; prm.read_jlo = c->d_jlo.p; prm.read_jcut = c->d_jcut.p; prm.codes = c->d_codes.p;
-    prm.flank = c->d_flank.p; prm.pile_l = c->d_pl.p; prm.pile_r = c->d_pr.p; prm.read_gap = c->d_rgap.p; prm.lfrf = c->d_lfrf.p; prm.meta = c->d_meta.p;
+    prm.read_flags = c->d_rfl.p; prm.read_jlo = c->d_jlo.p; prm.read_jcut = c->d_jcut.p;
+    prm.codes_pk = c->d_codes_pk.p; prm.read_pk_off = c->d_pkoff.p; prm.flank_pk = c->d_flank_pk.p;
+    prm.pile_l = c->d_pl.p; prm.pile_r = c->d_pr.p; prm.read_gap = c->d_rgap.p; prm.lfrf = c->d_lfrf.p; prm.meta = c->d_meta.p;
     prm.items = (const DevItem*)c->d_in.p; prm.in_arena = c->d_in.p + itemsBytes; prm.out_arena = c->d_out.p; prm.scratch = c->d_scratch.p;
     prm.counters = c->d_ctr.p;
     memcpy(prm.e_tab, c->hEtab, sizeof prm.e_tab);
