@@ -270,8 +270,14 @@ def main():
         sample = prepare_case(os.path.join(base, "sample"), SAMPLE, 1102)
         placements = ref_equivalent_placements(sample, os.path.join(base, "sample_work"))
         secs = run_step_reference(sample, cores)
+        # beside the as-shipped driver run (which sleeps 1 s after every worker start, FillGaps.cpp:675): the same workers
+        # started together (steady state), and the tuned -O2 flavour
+        steady = sum(fc.run_reference_workers_parallel(sample, mode, cores, "figbird_worker_O0") for mode in ("partial", "unmapped"))
+        tuned = sum(fc.run_reference_workers_parallel(sample, mode, cores, "figbird_worker_O2") for mode in ("partial", "unmapped"))
         line["cpu_baseline"] = {"value": placements / secs, "unit": unit, "cores": cores, "kind": "reference",
-                                "sample": "32-gap / 294 kbp sample of the c2 workload (same parameters), FillGaps partial+unmapped, as-shipped -O0 worker, numthreads=%d, %.1f s" % (cores, secs)}
+                                "sample": "32-gap / 294 kbp sample of the c2 workload (same parameters), FillGaps partial+unmapped, as-shipped -O0 worker, numthreads=%d, %.1f s" % (cores, secs),
+                                "steady_state": {"value": placements / steady, "seconds": steady, "note": "same sample, %d as-shipped -O0 worker processes started together (no driver sleep, no run-time compile)" % min(cores, 32)},
+                                "tuned": {"value": placements / tuned, "seconds": tuned, "note": "same, worker built -O2 -D_FORTIFY_SOURCE=0 (plain -O2 aborts, SURVEY 5)"}}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

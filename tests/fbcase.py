@@ -151,6 +151,31 @@ def run_reference_worker(case, mode, worker="figbird_worker_dump", extra_env=Non
     return {"seconds": time.time() - t0, "dir": run, "gapout": open(os.path.join(tmp, "gapout0.txt"), "rb").read()}
 
 
+def run_reference_workers_parallel(case, mode, threads, worker="figbird_worker_O0"):
+    """Steady-state flavour of the reference: `threads` worker processes (Figbird.cpp:6957-6973 CLI) started
+    together on a round-robin split of the gaps -- what FillGaps.cpp:668-679 does minus the run-time compile and the 1 s sleep
+    after every thread start.  Returns wall seconds."""
+    run = _fresh_tmp(case, mode, "refp")
+    tmp = os.path.join(run, "Temp")
+    ngaps = sum(1 for _ in open(os.path.join(tmp, "gapInfo.txt")))
+    threads = max(1, min(threads, ngaps))
+    loads = [[g for g in range(ngaps) if g % threads == t] for t in range(threads)]
+    with open(os.path.join(tmp, "gaploads.txt"), "w") as f:
+        for l in loads:
+            f.write("".join("%d\t" % g for g in l) + "\n")
+    a = fillgaps_argv(case, mode, tmp)
+    t0 = time.time()
+    procs = []
+    for t in range(threads):
+        argv = [os.path.join(REF, worker), a[0], a[1], a[2], a[3], a[4], a[5], str(t), str(len(loads[t])), a[7], a[8], a[9], a[10], a[11], "400", a[13], a[14]]
+        procs.append(subprocess.Popen(argv, cwd=run, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+    rc = [p.wait() for p in procs]
+    dt = time.time() - t0
+    if any(rc):
+        raise RuntimeError("reference worker failed: %r" % rc)
+    return dt
+
+
 def run_ours(case, mode, exe, threads=1, extra_env=None, name="ours"):
     run = _fresh_tmp(case, mode, name)
     env = dict(os.environ)
