@@ -9,7 +9,7 @@ import subprocess
 import sys
 import tempfile
 
-rep, kre, idx = sys.argv[1], sys.argv[2], sys.argv[3]
+rep, kre, idx = sys.argv[1], sys.argv[2], sys.argv[3]      # idx: launch index among the matching kernels, or "max" = the longest one
 lib = sys.argv[4] if len(sys.argv) > 4 else os.path.join(os.path.dirname(__file__), "..", "figbird_b200", "_build", "libfigbird_b200.so")
 top = int(sys.argv[5]) if len(sys.argv) > 5 else 40
 tmp = tempfile.mkdtemp()
@@ -28,6 +28,12 @@ for l in dis.split("\n"):
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/", l)
     if m and cur_fn and re.search(kre, cur_fn):
         line_of.setdefault(cur_fn, {})[int(m.group(1), 16)] = cur_line
+if idx == "max":
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout.decode()
+    rr = list(csv.reader(raw.split("\n")))
+    h = rr[0]; dcol = h.index("gpu__time_duration.sum"); ncol = h.index("Kernel Name")
+    cand = [(float(r[dcol]), k + 1) for k, r in enumerate([r for r in rr[2:] if len(r) == len(h) and re.search(kre, r[ncol])])]
+    idx = str(max(cand)[1])
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-id", "::regex:%s:%s" % (kre, idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout.decode()
 rows = list(csv.reader(out.split("\n")))
 hi = next(i for i, r in enumerate(rows) if "Instructions Executed" in r)

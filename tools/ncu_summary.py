@@ -32,6 +32,17 @@ for arg in sys.argv[1:]:
     hdr, units = rows[0], rows[1]
     body = [r for r in rows[2:] if len(r) == len(hdr)]
     d = hdr.index(KEYS["duration_ms"])
+    scale = {"nsecond": 1e-6, "usecond": 1e-3, "msecond": 1.0, "second": 1e3, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(units[d], 1.0)
+    for r in body:
+        r[d] = repr(float(r[d]) * scale)          # durations in ms whatever unit ncu chose for the column
+    units[d] = "ms"
+    bscale = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}
+    for name, tgt in ((KEYS["dram_read_mb"], 1.0), (KEYS["dram_write_kb"], 1e3)):
+        if name in hdr:
+            i = hdr.index(name); f = bscale.get(units[i], 1.0) * tgt
+            for r in body:
+                r[i] = repr(float(r[i]) * f)
+            units[i] = "Mbyte" if tgt == 1.0 else "Kbyte"
     best = max(body, key=lambda r: float(r[d]))
     rec = {"file": os.path.basename(path), "kernel": best[hdr.index("Kernel Name")]}
     for k, name in KEYS.items():
