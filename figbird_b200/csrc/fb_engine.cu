@@ -58,6 +58,14 @@ namespace {
 #ifndef FB_CTAS
 #define FB_CTAS 2
 #endif
+#ifndef FB_CHECK
+#define FB_CHECK 0      // 1: device-side bounds checks on the staged regions (diagnostic build; compute-sanitizer is not available on the pool)
+#endif
+#if FB_CHECK
+#define FBCHK(cond, what) do { if (!(cond)) { printf("FB_CHECK failed: %s (block %d thread %d)\n", what, (int)blockIdx.x, (int)threadIdx.x); __trap(); } } while (0)
+#else
+#define FBCHK(cond, what) do { } while (0)
+#endif
 #ifndef FB_PHASES
 #define FB_PHASES 0     // 1: thread 0 accumulates the clock cycles between the barriers of an EM round (diagnostic build)
 #endif
@@ -423,11 +431,13 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
         RC = (unsigned char*)CNT + al16(12 * nq);
         RC2 = (unsigned short*)(RC + (size_t)nq * mlp);         // [nq][mlp] code * S / 8: plane offset of the walk in units of 8 entries
         W = (double*)(RC + (size_t)nq * 3 * mlp);
+        FBCHK((unsigned char*)W <= chunkBase + chunkBytes, "chunk records + codes exceed the chunk region");
     };
     auto stageReads = [&](int q0, int q1) {   // read records and codes of the chunk
         const int nq = q1 - q0;
         carveChunk(nq);
         const int wb = mt.woff[q0], u1b = mt.u1[q0], u2b = mt.u2[q0];
+        FBCHK((unsigned char*)(W + (mt.woff[q1] - wb)) <= chunkBase + chunkBytes, "weight rows exceed the chunk region");
         for (int ql = tid; ql <= nq; ql += kThreads) {
             const int q = q0 + ql;
             RMeta r;
@@ -600,6 +610,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                     const bool rev = (r.packed >> 24) & FB_READ_REVERSE;
                     const unsigned char* rc = RC + ql * mlp;
                     const unsigned char* ga = G + ra; const unsigned char* gb = G + rb;
+                    FBCHK(ra + jlo >= 0 && ra + jhi <= rows && rb + jlo >= 0 && rb + jhi <= rows, "pass 2 leaves the gap string");
                     int j = jlo, steps = 0;
                     while (j < jhi) {
                         const int je = min(jhi, j + 4);
@@ -789,6 +800,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                     int x0cur = xm - m0 * Lg;          // placement whose segment contains read base js
                     int jw = (m0 + 1) * Lg - xm;       // read base at which the walk re-enters gap row 0 (> js)
                     const double2* ptr = UT + xm;      // + j: cyclically extended table, plane 0
+                    FBCHK(xm >= 0 && xm + je <= S && js >= 0 && je <= mlp, "walk leaves the extended table");
                     const unsigned short* rc = RC2 + ql * mlp;
                     // me[j] = e of read base j: kernel-parameter (constant bank) table, or shared memory when reads are longer than it
                     const bool revRead = (r.packed >> 24) & FB_READ_REVERSE;
@@ -806,6 +818,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                     auto wrapN = [&](int j) {
                         const bool w = (j == jw);       // the walk re-enters gap row 0: the running product belongs to placement x0cur
                         const bool st = w && ((unsigned)slotN < (unsigned)nAct);
+                        FBCHK(!st || wtr(slotN, np) < ((n + 3) & ~3), "flush slot outside the weight row");
                         if (TSMEM) {
                             const unsigned wa = (unsigned)__cvta_generic_to_shared(Wq) + ((unsigned)wtr(slotN, np) << 3);
                             asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p st.shared.f64 [%1], %2; }" :: "r"((unsigned)st), "r"(wa), "d"(acc) : "memory");
@@ -901,6 +914,7 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                             const unsigned char* rc = RC + ql * mlp;
                             const double* wr = W + r.wrel;
                             const int np = (n + 3) >> 2;
+                            FBCHK(r.wrel >= 0 && (unsigned char*)(wr + ((n + 3) & ~3)) <= chunkBase + chunkBytes, "gather row outside the chunk region");
                             auto ld = [&](int i) -> double { return ((unsigned)i < (unsigned)n) ? wr[wtr(i, np)] : 0.0; };
                             int i0 = x - ja - xlo;                 // weight index of row x at read base ja; row x+b: i0 + b
                             double w[B];
