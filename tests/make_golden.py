@@ -25,6 +25,11 @@ CASES = {
     "g3": dict(gen={"genome": 40000, "gaplist": "15,90,260", "seed": 23, "cov": 30, "sd": 50}, readlen=150, insert=500),
     # BASELINE configs[2]'s second library (3500 bp insert, maxDistance 4025): every offset of the window is admissible
     "g4": dict(gen={"genome": 50000, "gaplist": "20,110", "seed": 24, "cov": 20, "sd": 350}, readlen=100, insert=3500),
+    # large gaps (N-run > unm_limit 400: one candidate, host-driven rounds with border updates, Figbird.cpp:4029-4376) at
+    # BASELINE configs[3] read parameters
+    "g5": dict(gen={"genome": 60000, "gaplist": "1200,2500,800", "seed": 51, "cov": 30, "sd": 50}, readlen=150, insert=500),
+    # BASELINE configs[4] regime: gaps of several kbp under the 3500 bp jump library
+    "g6": dict(gen={"genome": 90000, "gaplist": "5000,3000,1500", "seed": 52, "cov": 20, "sd": 350}, readlen=100, insert=3500),
 }
 
 
