@@ -10,6 +10,7 @@
 // including its quirks (the MD string is compared with the CIGAR of an error-free read, so every read takes
 // the error path, :297; soft clips count as insertions, :339; computeErrorProb does not split CIGARs at 'S', :988).
 #include <cmath>
+#include <cstdint>
 #include <cstdlib>
 #include <chrono>
 #include <cstring>
@@ -40,7 +41,7 @@ struct Tokens {
 
 inline int baseIndex(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 4; }
 
-struct Stats {
+struct alignas(128) Stats {      // (one per parsing thread, side by side in a vector: no shared cache lines)
     int maxReadLength, MAX_INSERT_SIZE, maxInsertSize;
     std::vector<long> insertCounts;
     long errorTypes[5][5]; long baseCounts[5];
@@ -132,6 +133,80 @@ bool splitMyout(char* line, SamFields& f, char* mdKeep /*persisting MD buffer*/)
     return true;
 }
 
+// ---- fast path for regular lines.  Both passes spend their time tokenising; a line that matches the strict grammar below
+// (what Preprocess writes for an ungapped, unclipped alignment: Preprocess.cpp:412-416) is parsed in place, without copies,
+// and handed to the same callbacks as the generic strtok-style code, so the arithmetic is shared.  Anything else -- soft
+// clips, indels, '^' in MD, missing or reordered tags, over-long lines -- takes the generic path.
+//   qname \t flag \t rname \t pos \t <n>M \t [-]tlen \t seq \t qual \t MD:Z:[0-9ACGTN]+ \t IH:i:<n> \n
+struct FastLine { const char* qname; int qlen; int flag; long rname; int tlen; const char* seq; int seqLen; const char* md; int mdLen; int nh; };
+
+// what pass 2 needs of a regular line, kept from pass 1 (offsets from the line start)
+struct LineRec { uint16_t ok, qlen, flag, seqOff, seqLen, mdOff, mdLen; int tlen; };
+
+inline bool fastDigits(const char*& p, long& v) {      // 1..9 digits followed by a tab (consumed); value as atoi / atol give it
+    const char* q = p; long x = 0;
+    while (*q >= '0' && *q <= '9' && q - p < 10) x = x * 10 + (*q++ - '0');
+    if (q == p || q - p > 9 || *q != '\t') return false;
+    v = x; p = q + 1; return true;
+}
+
+inline bool fastSplit(const char* ln, const char* end, FastLine& f) {      // end: one past the last byte of the text
+    const char* const e = (const char*)memchr(ln, '\n', (size_t)(end - ln));
+    if (!e || e - ln > 1022 || e == ln) return false;      // no newline (last line), or fgets(1024) would have cut it: generic path
+    auto field = [&](const char* p) -> const char* { return (const char*)memchr(p, '\t', (size_t)(e - p)); };      // the tab that ends the field at p
+    const char* p = ln;
+    if (*p == '\t') return false;                           // strtok would skip leading tabs
+    const char* t = field(p); if (!t) return false;
+    f.qname = p; f.qlen = (int)(t - p); p = t + 1;
+    long v;
+    if (!fastDigits(p, v)) return false; f.flag = (int)v;
+    if (!fastDigits(p, v)) return false; f.rname = v;
+    if (!fastDigits(p, v)) return false;                         // pos
+    if (!(*p >= '0' && *p <= '9')) return false;
+    while (*p >= '0' && *p <= '9') p++;
+    if (p[0] != 'M' || p[1] != '\t') return false;               // CIGAR = one M operation
+    p += 2;
+    const bool neg = (*p == '-'); if (neg) p++;
+    if (!fastDigits(p, v)) return false; f.tlen = neg ? -(int)v : (int)v;
+    t = field(p); if (!t || t == p) return false;
+    f.seq = p; f.seqLen = (int)(t - p); p = t + 1;
+    t = field(p); if (!t || t == p) return false;               // qual
+    p = t + 1;
+    if (!(p[0] == 'M' && p[1] == 'D' && p[2] == ':' && p[3] == 'Z' && p[4] == ':')) return false;
+    f.md = p; p += 5;
+    const char* body = p;
+    for (;; p++) { const char c = *p; if ((c >= '0' && c <= '9') || c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'N') continue; break; }
+    if (p == body || *p != '\t') return false;
+    f.mdLen = (int)(p - f.md); if (f.mdLen > 990) return false; p++;
+    if (!(p[0] == 'I' && p[1] == 'H' && p[2] == ':' && p[3] == 'i' && p[4] == ':')) return false;
+    p += 5;
+    const char* d = p; long nh = 0;
+    while (*p >= '0' && *p <= '9' && p - d < 10) nh = nh * 10 + (*p++ - '0');
+    if (p == d || p - d > 9 || p != e) return false;
+    f.nh = (int)nh;
+    return true;
+}
+
+// walkMD on the body of a regular MD tag (digits and ACGTN only), no insertions in the read: same state machine, in place.
+template <class OnMis>
+inline void fastWalkMD(const char* body, int bl, OnMis onMis) {
+    auto isDelim = [](char c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'N'; };
+    int index = 0, pos = 0; long totalLength = 0;
+    for (;;) {
+        while (pos < bl && isDelim(body[pos])) pos++;
+        if (pos >= bl) break;
+        int val = 0; const int t0 = pos; bool big = false;
+        while (pos < bl && !isDelim(body[pos])) { if (pos - t0 < 9) val = val * 10 + (body[pos] - '0'); else big = true; pos++; }
+        if (big) val = atoi(std::string(body + t0, body + pos).c_str());
+        totalLength += pos - t0;
+        if (totalLength < bl) {
+            const char from = body[totalLength];
+            if (isDelim(from)) { totalLength++; index += val + 1; onMis(from, index, 0); }
+            else break;
+        }
+    }
+}
+
 }  // namespace
 
 bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err) {
@@ -155,6 +230,7 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err) 
     const double inputMean = a.setInputMean == 1 ? (double)a.insertSizeMean : 0.0;   // Figbird.cpp:6973
 
     const bool timing = getenv("FIGBIRD_MODEL_TIMING") != nullptr;
+    const bool useFast = getenv("FIGBIRD_MODEL_GENERIC") == nullptr;      // tests compare the two parsers
     auto tnow = [] { return std::chrono::steady_clock::now(); };
     auto tprev = tnow();
     auto lap = [&](const char* what) { if (timing) { auto t = tnow(); fprintf(stderr, "learnModel %-10s %.3f s\n", what, std::chrono::duration<double>(t - tprev).count()); tprev = t; } };
@@ -166,6 +242,7 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err) 
     std::vector<char*> lines;
     struct Mapping { void* p = nullptr; size_t len = 0; ~Mapping() { if (p) munmap(p, len); } } mapping;
     char* textBase = nullptr;
+    const char* textEnd = nullptr;
     {
         fseek(mf, 0, SEEK_END); const long n = ftell(mf); fseek(mf, 0, SEEK_SET);
         int rt = (int)std::thread::hardware_concurrency();
@@ -173,6 +250,7 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err) 
         rt = std::max(1, std::min(rt, (int)(n / (8 << 20)) + 1));
         const int fd = fileno(mf);
         long total = n;
+        struct SetEnd { const char*& e; char*& b; long n; ~SetEnd() { e = b ? b + n : nullptr; } } setEnd{textEnd, textBase, n};
         // map the page cache instead of copying it; the zero tail of the last page is the terminating NUL
         // (a file that ends exactly on a page boundary takes the copying path)
         if (n > 0 && (n % 4096) != 0) {
@@ -223,8 +301,41 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err) 
     // ---- pass 1: processMapping.  The statistics are integer counts, so the file is cut into blocks that are
     // counted on separate threads and summed -- identical to the sequential result as long as every line carries its
     // own MD/IH tags and no insert size hits the histogram-growth corner (Figbird.cpp:203); otherwise redo it serially.
-    auto pass1Line = [&](Stats& st, char* mdKeep, std::vector<char>& scratch, char* ln, bool& irregular) {
+    std::vector<LineRec> recs;
+    if (useFast) recs.resize(lines.size());      // (zero-filled pages are first touched by the thread that owns the block)
+    auto pass1Line = [&](Stats& st, char* mdKeep, std::vector<char>& scratch, char* ln, bool& irregular, LineRec* rec) {
+        if (rec) rec->ok = 0;
         if (ln[0] == '@') return;
+        FastLine fl;
+        if (useFast && fastSplit(ln, textEnd, fl)) {
+            if (rec && fl.flag < 65536) { rec->ok = 1; rec->qlen = (uint16_t)fl.qlen; rec->flag = (uint16_t)fl.flag; rec->seqOff = (uint16_t)(fl.seq - ln); rec->seqLen = (uint16_t)fl.seqLen;
+                                          rec->mdOff = (uint16_t)(fl.md - ln); rec->mdLen = (uint16_t)fl.mdLen; rec->tlen = fl.tlen; }
+            memcpy(mdKeep, fl.md, (size_t)fl.mdLen); mdKeep[fl.mdLen] = 0;      // (a later irregular line may inherit it, as in the generic path)
+            if (fl.nh != 1) return;
+            if (fl.rname >= 0 && fl.rname < (long)sc.seq.size() && (double)sc.seq[fl.rname].size() > inputMean) {
+                if (fl.tlen >= st.maxInsertSize && fl.tlen <= st.MAX_INSERT_SIZE) irregular = true;
+                bumpInsert(st, fl.tlen);
+            }
+            const int strand = (fl.flag & 16) >> 4;
+            const int readLength = fl.seqLen;
+            {   // (independent counters instead of one increment chain through memory)
+                long nA = 0, nC = 0, nG = 0, nT = 0;
+                for (int i = 0; i < readLength; i++) { const char c = fl.seq[i]; nA += c == 'A'; nC += c == 'C'; nG += c == 'G'; nT += c == 'T'; }
+                st.baseCounts[0] += nA; st.baseCounts[1] += nC; st.baseCounts[2] += nG; st.baseCounts[3] += nT; st.baseCounts[4] += readLength - nA - nC - nG - nT;
+            }
+            if (readLength > RL) { st.uniqueMappedReads++; return; }
+            st.readLengths[readLength - 1]++;
+            fastWalkMD(fl.md + 5, fl.mdLen - 5, [&](char from, int idx, int cur) {
+                int ri = idx - 1 + cur;
+                char to = (ri >= 0 && ri < readLength) ? fl.seq[ri] : 'N';
+                int at = strand == 0 ? ri : readLength - idx - cur;
+                if (at >= 0 && at < RL) st.errorPos[at]++;
+                int fi = baseIndex(from), ti = baseIndex(to);
+                if (fi != ti) st.errorTypes[fi][ti]++;
+            });
+            st.uniqueMappedReads++;
+            return;
+        }
         size_t len = strcspn(ln, "\n"); if (len > 1022) len = 1022;   // fgets(1024)
         scratch.assign(ln, ln + len + 1); scratch[len] = '\n'; scratch.push_back(0);
         SamFields f;
@@ -291,7 +402,7 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err) 
             zeroStats(part[t]);
             std::vector<char> scratch(2048); char mdKeep[1000]; mdKeep[0] = 0; bool ir = false;
             const size_t lo = lines.size() * t / nThreads, hi = lines.size() * (t + 1) / nThreads;
-            for (size_t i = lo; i < hi; i++) pass1Line(part[t], mdKeep, scratch, lines[i], ir);
+            for (size_t i = lo; i < hi; i++) pass1Line(part[t], mdKeep, scratch, lines[i], ir, useFast ? &recs[i] : nullptr);
             irr[t] = ir;
         });
         for (auto& t : th) t.join();
@@ -308,7 +419,7 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err) 
     }
     if (nThreads <= 1 || irregularAny) {
         std::vector<char> scratch(2048); char mdKeep[1000]; mdKeep[0] = 0; bool ir = false;
-        for (char* ln : lines) pass1Line(s, mdKeep, scratch, ln, ir);
+        for (size_t i = 0; i < lines.size(); i++) pass1Line(s, mdKeep, scratch, lines[i], ir, useFast ? &recs[i] : nullptr);
     }
 
     lap("pass1");
@@ -377,6 +488,14 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err) 
         if (effectiveLengths[insertSize] == -1) effectiveLengths[insertSize] = compute();
         return effectiveLengths[insertSize];
     };
+    auto misEp = [&](long double& ep, char from, int idx, int cur, const char* read, int readLength, int strand) {
+        int ri = idx - 1 + cur;
+        char to = (ri >= 0 && ri < readLength) ? read[ri] : '\0';
+        int i = strand == 0 ? ri : readLength - idx - cur;
+        if (i >= 0 && i < RL) ep = ep * m.errorPosDist[i] / (1 - m.errorPosDist[i] - m.inPosDist[i] - m.delPosDist[i]);
+        int fi = baseIndex(from), ti = baseIndex(to);
+        if (fi != ti) ep *= baseErrorRates[fi] * m.errorTypeProbs[fi][ti];
+    };
     auto errorProb = [&](const char* cigar, const char* md, const char* read, int strand) -> long double {
         const unsigned long readLength = strlen(read);
         long double ep = (readLength >= 1 && (int)readLength <= RL) ? noErrorProbs[readLength - 1] : 0;
@@ -398,65 +517,81 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err) 
                     ep = ep * m.delPosDist[i] * delLengthDist[n - 1] / (1 - m.errorPosDist[i] - m.inPosDist[i] - m.delPosDist[i]);
             }
         });
-        walkMD(md, inserts, [&](char from, int idx, int cur) {
-            int ri = idx - 1 + cur;
-            char to = (ri >= 0 && ri < (int)readLength) ? read[ri] : '\0';
-            int i = strand == 0 ? ri : (int)readLength - idx - cur;
-            if (i >= 0 && i < RL) ep = ep * m.errorPosDist[i] / (1 - m.errorPosDist[i] - m.inPosDist[i] - m.delPosDist[i]);
-            int fi = baseIndex(from), ti = baseIndex(to);
-            if (fi != ti) ep *= baseErrorRates[fi] * m.errorTypeProbs[fi][ti];
-        });
+        walkMD(md, inserts, [&](char from, int idx, int cur) { misEp(ep, from, idx, cur, read, (int)readLength, strand); });
         return ep;
+    };
+    auto errorProbFast = [&](const FastLine& fl) -> long double {      // the same for a regular line (one M operation, no '^')
+        const int readLength = fl.seqLen, strand = (fl.flag & 16) >> 4;
+        long double ep = (readLength >= 1 && readLength <= RL) ? noErrorProbs[readLength - 1] : 0;
+        fastWalkMD(fl.md + 5, fl.mdLen - 5, [&](char from, int idx, int cur) { misEp(ep, from, idx, cur, fl.seq, readLength, strand); });
+        return ep;
+    };
+    // one line of a pair: read name, template length and error probability (fast or generic parse)
+    struct P2Line { const char* q; int qn; int tlen; long double e; };
+    auto parseP2 = [&](size_t li, std::vector<char>& b, char* mdKeep, P2Line& o) -> bool {
+        char* const l = lines[li];
+        FastLine fl;
+        if (useFast && recs[li].ok) {
+            const LineRec& r = recs[li];
+            fl.qname = l; fl.qlen = r.qlen; fl.flag = r.flag; fl.tlen = r.tlen; fl.seq = l + r.seqOff; fl.seqLen = r.seqLen; fl.md = l + r.mdOff; fl.mdLen = r.mdLen;
+            memcpy(mdKeep, fl.md, (size_t)fl.mdLen); mdKeep[fl.mdLen] = 0;
+            o.q = fl.qname; o.qn = fl.qlen; o.tlen = fl.tlen; o.e = errorProbFast(fl);
+            return true;
+        }
+        size_t n = strcspn(l, "\n");
+        if (n > 1022) n = 1022;
+        b.assign(l, l + n + 1); b[n] = '\n'; b.push_back(0);
+        SamFields f;
+        if (!splitMyout(b.data(), f, mdKeep)) return false;
+        o.q = l + (f.qname - b.data()); o.qn = (int)strlen(f.qname); o.tlen = f.tlen;
+        o.e = errorProb(f.cigar, mdKeep, f.seq, (f.flag & 16) >> 4);
+        return true;
     };
 
     long gapProbs[1000] = {0};
     lap("tables");
     if (nThreads <= 1 || irregularAny) {
-        std::string pre1 = "*", pre2 = "*";
+        const char* p1 = "*"; int pn1 = 1; const char* p2 = "*"; int pn2 = 1;
+        auto same = [](const char* a, int an, const char* b, int bn) { return an == bn && memcmp(a, b, an) == 0; };
         long double tempProb = 0, gapProb = 0;
         char md1[1000], md2[1000]; md1[0] = md2[0] = 0;
         std::vector<char> b1(2048), b2(2048);
         size_t li = 0;
         while (li < lines.size()) {
-            char* l1 = lines[li++];
-            if (l1[0] == '@') continue;
+            const size_t i1 = li++;
+            if (lines[i1][0] == '@') continue;
             if (li >= lines.size()) break;
-            char* l2 = lines[li++];
-            size_t n1 = strcspn(l1, "\n"), n2 = strcspn(l2, "\n");
-            if (n1 > 1022) n1 = 1022; if (n2 > 1022) n2 = 1022;
-            b1.assign(l1, l1 + n1 + 1); b1[n1] = '\n'; b1.push_back(0);
-            b2.assign(l2, l2 + n2 + 1); b2[n2] = '\n'; b2.push_back(0);
-            SamFields f1, f2;
-            if (!splitMyout(b1.data(), f1, md1) || !splitMyout(b2.data(), f2, md2)) continue;
-            int insertSize = std::max(f1.tlen, f2.tlen);
+            const size_t i2 = li++;
+            P2Line x1, x2;
+            if (!parseP2(i1, b1, md1, x1) || !parseP2(i2, b2, md2, x2)) continue;
+            int insertSize = std::max(x1.tlen, x2.tlen);
             long double insertSizeProb = 0;
             if (insertSize >= 0 && insertSize < MI) insertSizeProb = insertLengthDist[insertSize];
             if (insertSizeProb == 0) insertSizeProb = 1 / (double)s.uniqueMappedReads;
-            long double e1 = errorProb(f1.cigar, md1, f1.seq, (f1.flag & 16) >> 4);
-            long double e2 = errorProb(f2.cigar, md2, f2.seq, (f2.flag & 16) >> 4);
             long eff = effLen(insertSize);
-            long double prob = (1 / (long double)(eff)) * insertSizeProb * e1 * e2;
-            if (pre1 == f1.qname && pre2 == f2.qname) {
-                if (tempProb < prob) { tempProb = prob; gapProb = e2; }
-            } else if (pre1 != "*" && pre2 != "*") {
+            long double prob = (1 / (long double)(eff)) * insertSizeProb * x1.e * x2.e;
+            if (same(p1, pn1, x1.q, x1.qn) && same(p2, pn2, x2.q, x2.qn)) {
+                if (tempProb < prob) { tempProb = prob; gapProb = x2.e; }
+            } else if (!same(p1, pn1, "*", 1) && !same(p2, pn2, "*", 1)) {
                 int gapIndex = -std::log10(gapProb);
                 gapIndex++;
                 if (gapIndex < 1000 && gapIndex >= 0) gapProbs[gapIndex]++; else gapProbs[999]++;
-                tempProb = prob; gapProb = e2;
-            } else { tempProb = prob; gapProb = e2; }
-            pre1 = f1.qname; pre2 = f2.qname;
+                tempProb = prob; gapProb = x2.e;
+            } else { tempProb = prob; gapProb = x2.e; }
+            p1 = x1.q; pn1 = x1.qn; p2 = x2.q; pn2 = x2.qn;
         }
     }
     else {
         // same histogram, pairs evaluated on threads (each pair's probabilities depend only on its two lines), then the
         // sequential read-name grouping of Figbird.cpp:1290-1349 over the stored results
         struct PairRes { const char* q1; const char* q2; int n1, n2; long double e2, prob; bool ok; };
-        std::vector<std::pair<char*, char*>> pairs;
+        std::vector<std::pair<size_t, size_t>> pairs;
+        pairs.reserve(lines.size() / 2 + 1);
         for (size_t li = 0; li < lines.size();) {
-            char* l1 = lines[li++];
-            if (l1[0] == '@') continue;
+            const size_t i1 = li++;
+            if (lines[i1][0] == '@') continue;
             if (li >= lines.size()) break;
-            pairs.emplace_back(l1, lines[li++]);
+            pairs.emplace_back(i1, li++);
         }
         std::vector<PairRes> res(pairs.size());
         std::vector<std::thread> th;
@@ -465,23 +600,17 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err) 
             std::vector<char> b1(2048), b2(2048);
             const size_t lo = pairs.size() * t / nThreads, hi = pairs.size() * (t + 1) / nThreads;
             for (size_t i = lo; i < hi; i++) {
-                char* l1 = pairs[i].first; char* l2 = pairs[i].second;
-                size_t n1 = strcspn(l1, "\n"), n2 = strcspn(l2, "\n");
-                if (n1 > 1022) n1 = 1022;
-                if (n2 > 1022) n2 = 1022;
-                b1.assign(l1, l1 + n1 + 1); b1[n1] = '\n'; b1.push_back(0);
-                b2.assign(l2, l2 + n2 + 1); b2[n2] = '\n'; b2.push_back(0);
-                SamFields f1, f2;
                 PairRes& r = res[i];
-                r.ok = splitMyout(b1.data(), f1, md1) && splitMyout(b2.data(), f2, md2);
+                P2Line x1, x2;
+                r.ok = parseP2(pairs[i].first, b1, md1, x1) && parseP2(pairs[i].second, b2, md2, x2);
                 if (!r.ok) continue;
-                r.q1 = l1; r.n1 = (int)strlen(f1.qname); r.q2 = l2; r.n2 = (int)strlen(f2.qname);
-                int insertSize = std::max(f1.tlen, f2.tlen);
+                r.q1 = x1.q; r.n1 = x1.qn; r.q2 = x2.q; r.n2 = x2.qn;
+                int insertSize = std::max(x1.tlen, x2.tlen);
                 long double insertSizeProb = 0;
                 if (insertSize >= 0 && insertSize < MI) insertSizeProb = insertLengthDist[insertSize];
                 if (insertSizeProb == 0) insertSizeProb = 1 / (double)s.uniqueMappedReads;
-                long double e1 = errorProb(f1.cigar, md1, f1.seq, (f1.flag & 16) >> 4);
-                r.e2 = errorProb(f2.cigar, md2, f2.seq, (f2.flag & 16) >> 4);
+                long double e1 = x1.e;
+                r.e2 = x2.e;
                 long eff;
                 if (insertSize < 0) eff = totalContigLength;
                 else { eff = 0; for (auto& q : sc.seq) if ((long)q.size() >= insertSize) eff += ((long)q.size() - insertSize + 1); }
@@ -489,21 +618,38 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err) 
             }
         });
         for (auto& t : th) t.join();
-        const char* p1 = "*"; int pn1 = 1; const char* p2 = "*"; int pn2 = 1;
-        long double tempProb = 0, gapProb = 0;
+        // The grouping of Figbird.cpp:1290-1349 over the stored results: a group = a maximal run of consecutive pairs with the same
+        // two read names; when the next group begins, the e2 of the group's most probable pair (first maximum) is histogrammed,
+        // unless one of the group's names is "*" (the initial state of the reference's loop); the last group never is.  Groups are
+        // independent, so every thread takes the groups that start in its block (it may read past the block's end).
         auto same = [](const char* a, int an, const char* b, int bn) { return an == bn && memcmp(a, b, an) == 0; };
-        for (const PairRes& r : res) {
-            if (!r.ok) continue;
-            if (same(p1, pn1, r.q1, r.n1) && same(p2, pn2, r.q2, r.n2)) {
-                if (tempProb < r.prob) { tempProb = r.prob; gapProb = r.e2; }
-            } else if (!same(p1, pn1, "*", 1) && !same(p2, pn2, "*", 1)) {
-                int gapIndex = -std::log10(gapProb);
-                gapIndex++;
-                if (gapIndex < 1000 && gapIndex >= 0) gapProbs[gapIndex]++; else gapProbs[999]++;
-                tempProb = r.prob; gapProb = r.e2;
-            } else { tempProb = r.prob; gapProb = r.e2; }
-            p1 = r.q1; pn1 = r.n1; p2 = r.q2; pn2 = r.n2;
-        }
+        std::vector<uint32_t> okIdx; okIdx.reserve(res.size());
+        for (size_t i = 0; i < res.size(); i++) if (res[i].ok) okIdx.push_back((uint32_t)i);
+        const size_t M = okIdx.size();
+        std::vector<std::vector<long>> hist(nThreads, std::vector<long>(1000 + 16, 0));
+        th.clear();
+        for (int t = 0; t < nThreads; t++) th.emplace_back([&, t] {
+            long* const h = hist[t].data();
+            const size_t lo = M * t / nThreads, hi = M * (t + 1) / nThreads;
+            for (size_t i = lo; i < hi; i++) {
+                const PairRes& r = res[okIdx[i]];
+                if (i > 0) { const PairRes& q = res[okIdx[i - 1]]; if (same(q.q1, q.n1, r.q1, r.n1) && same(q.q2, q.n2, r.q2, r.n2)) continue; }
+                long double tempProb = r.prob, gapProb = r.e2;
+                size_t j = i + 1;
+                for (; j < M; j++) {
+                    const PairRes& x = res[okIdx[j]];
+                    if (!(same(r.q1, r.n1, x.q1, x.n1) && same(r.q2, r.n2, x.q2, x.n2))) break;
+                    if (tempProb < x.prob) { tempProb = x.prob; gapProb = x.e2; }
+                }
+                if (j < M && !same(r.q1, r.n1, "*", 1) && !same(r.q2, r.n2, "*", 1)) {
+                    int gapIndex = -std::log10(gapProb);
+                    gapIndex++;
+                    if (gapIndex < 1000 && gapIndex >= 0) h[gapIndex]++; else h[999]++;
+                }
+            }
+        });
+        for (auto& t : th) t.join();
+        for (int t = 0; t < nThreads; t++) for (int i = 0; i < 1000; i++) gapProbs[i] += hist[t][i];
     }
     lap("pass2");
     {   // Figbird.cpp:7155-7178

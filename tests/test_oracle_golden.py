@@ -63,3 +63,76 @@ def test_threaded_model_learning_is_identical(case, mode):
     exp = gu.expected(case, mode)
     assert o["gapout.txt"] == exp["gapout.txt"]
     assert gu.model_lines(model) == gu.model_lines(os.path.join(case, "expected", mode, "model.txt"))
+
+
+def _perturbed_myout(src, dst):
+    """myout.sam of a golden case with irregular lines mixed in (whole pairs, so the pairing of pass 2 is kept): soft clips,
+    indels, '^' in MD, adjacent MD letters, a pair without tags (inherits the previous MD), extra tags, reordered tags, a
+    quality string that looks like a tag, an over-long line, a multi-mapped pair, and a last line without a newline."""
+    lines = open(src).read().split("\n")
+    lines = [l for l in lines if l]
+    out = []
+    def edit(l, **kw):
+        f = l.split("\t")
+        for k, v in kw.items():
+            f[{"cigar": 4, "seq": 6, "qual": 7, "md": 8, "ih": 9, "tlen": 5, "flag": 1}[k]] = v
+        return f
+    for i in range(0, len(lines) - 1, 2):
+        a, b = lines[i], lines[i + 1]
+        k = (i // 2) % 40
+        if k == 3:
+            a = "\t".join(edit(a, cigar="20S80M"))
+        elif k == 5:
+            b = "\t".join(edit(b, cigar="50M2I48M", md="MD:Z:30A67"))
+        elif k == 7:
+            a = "\t".join(edit(a, cigar="40M3D60M", md="MD:Z:40^ACG60"))
+        elif k == 9:
+            b = "\t".join(edit(b, md="MD:Z:^AC100"))
+        elif k == 11:
+            a = "\t".join(edit(a, md="MD:Z:10AC5T82"))
+        elif k == 13:
+            a, b = "\t".join(a.split("\t")[:8]), "\t".join(b.split("\t")[:8])
+        elif k == 15:
+            a = a + "\tXS:i:5"
+        elif k == 17:
+            f = b.split("\t"); b = "\t".join(f[:8] + [f[9], f[8]])
+        elif k == 19:
+            f = a.split("\t"); f[7] = "MD" + f[7][2:]; a = "\t".join(f)
+        elif k == 21:
+            f = b.split("\t"); f[7] = "IH:i:" + f[7][5:]; b = "\t".join(f)
+        elif k == 23:
+            f = a.split("\t"); f[0] = f[0] + "x" * 900; a = "\t".join(f)
+        elif k == 25:
+            a, b = "\t".join(edit(a, ih="IH:i:2")), "\t".join(edit(b, ih="IH:i:2"))
+            out += [a, b]      # the same pair twice: one group for the grouping of pass 2
+        elif k == 27:
+            a = "\t".join(edit(a, md="MD:Z:0A0C0G97"))
+        elif k == 29:
+            b = "\t".join(edit(b, seq=b.split("\t")[6][:60] + "N" * 40))
+        out += [a, b]
+    open(dst, "w").write("\n".join(out))      # (no trailing newline)
+
+
+@pytest.mark.parametrize("threads", ["1", "5"])
+def test_fast_model_parser_equals_generic_on_irregular_input(case, threads):
+    """learnModel's in-place parser for regular lines and its strtok-style generic parser (the restatement of
+    Figbird.cpp:846-1376) give the same tables and cut-off on a myout.sam with irregular lines mixed in."""
+    import shutil
+    work = os.path.join(case, "perturbed_%s" % threads)
+    shutil.rmtree(work, ignore_errors=True)
+    os.makedirs(os.path.join(work, "Temp"))
+    for f in ("gapInfo.txt", "stat.txt", "stat2.txt"):
+        shutil.copy(os.path.join(case, "unmapped", "Temp", f), os.path.join(work, "Temp", f))
+    my = os.path.join(work, "myout.sam")
+    _perturbed_myout(os.path.join(case, "unmapped", "myout.sam"), my)
+    argv = fc.fillgaps_argv(case, "unmapped", os.path.join(work, "Temp"))
+    argv[7] = my
+    argv[9] = os.path.join(work, "nogaps") + "/"
+    dumps = {}
+    for name, env in (("fast", {}), ("generic", {"FIGBIRD_MODEL_GENERIC": "1"})):
+        d = os.path.join(work, "model_%s.txt" % name)
+        e = dict(os.environ); e.update(env); e.update({"FIGBIRD_DUMP_MODEL": d, "FIGBIRD_HOST_THREADS": threads, "FIGBIRD_MODEL_BLOCK": "64"})
+        fc.sh([fc.oracle_exe()] + argv, cwd=work, env=e)
+        dumps[name] = open(d).read()
+    assert len(dumps["fast"].split("\n")) > 100
+    assert dumps["fast"] == dumps["generic"]
