@@ -75,6 +75,9 @@ namespace {
 #ifndef FB_FUSE2
 #define FB_FUSE2 0      // same for pass 2
 #endif
+#ifndef FB_PREF
+#define FB_PREF 1       // 1: integer mismatch prefilter in front of the pass-2 products
+#endif
 constexpr int kThreads = FB_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxSmem = 200 * 1024;      // dynamic shared memory we opt in to (227 KB is the sm_100 limit)
@@ -100,6 +103,7 @@ struct DevModel {
     double etp[25];
     int tmin, tmax, max_read_len;
     int prunable;                           // every pass-2 factor is in [0, 1]: running products are monotone
+    int mis_a;                              // every pass-2 mismatch factor is <= 2^-mis_a (0: unknown, no integer prefilter)
     double accept_min_p;
 };
 
@@ -202,6 +206,18 @@ __device__ __forceinline__ int wtr(int i, int np) { return FB_WTR ? (i & 3) * np
 
 // base code i of a packed sequence (A0 C1 G2 T3, 4 = N / other)
 __device__ __forceinline__ int pkCode(const uint2* p, int i) { const uint2 w = p[i >> 4]; const int sft = i & 15; return ((w.y >> sft) & 1u) ? 4 : (int)((w.x >> (2 * sft)) & 3u); }
+
+// eight consecutive code bytes from an arbitrarily aligned address (three aligned words + byte permutes)
+__device__ __forceinline__ void load8(const unsigned char* p, unsigned& lo, unsigned& hi) {
+    const unsigned sh = (unsigned)((size_t)p & 3);
+    const unsigned* w = (const unsigned*)(p - sh);
+    const unsigned w0 = w[0], w1 = w[1], w2 = w[2];
+    const unsigned sel = 0x3210u + 0x1111u * sh;
+    lo = __byte_perm(w0, w1, sel); hi = __byte_perm(w1, w2, sel);
+}
+__device__ __forceinline__ int mismatches8(unsigned alo, unsigned ahi, unsigned blo, unsigned bhi) {
+    return __popc(__vcmpne4(alo, blo) & 0x01010101u) + __popc(__vcmpne4(ahi, bhi) & 0x01010101u);
+}
 
 // E[j] = sum_{k<4, k!=j} P[k]*ETP[k][j] in k order (Figbird.cpp:2118-2137)
 __device__ __forceinline__ void errRow(const double* etp, const double p[4], double e[5]) {
@@ -603,8 +619,27 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                 const int ia = ch * 64 + lane, ib = ia + 32;
                 const int xa = xlo + ia, xb = xlo + ib;
                 const bool ina = ia < n, inb = ib < n;
-                const bool acta = ina && xa != x1, actb = inb && xb != x1;
+                bool acta = ina && xa != x1, actb = inb && xb != x1;
                 double pa = 1.0, pb = 1.0;
+#if FB_PREF
+                // Integer prefilter.  Every factor is <= 1 and a mismatch factor is <= 2^-mis_a, so a placement with M mismatches
+                // among its first scored bases has a product <= 2^(-mis_a * M): with thr >= 2^ilogb(thr) it cannot reach thr once
+                // mis_a * M > -ilogb(thr).  Such placements are dropped before any FP64 work (they could only lose).
+                if (m.prunable && m.mis_a > 0 && thr > 0.0 && jhi - jlo >= 8) {
+                    const int Mthr = max(1, (-ilogb(thr)) / m.mis_a + 1);
+                    const unsigned char* rq = RC + ql * mlp + jlo;
+                    const unsigned char* qa = G + F + (ina ? xa : xlo) + jlo; const unsigned char* qb = G + F + (inb ? xb : (ina ? xa : xlo)) + jlo;
+                    unsigned r0, r1, a0, a1, b0, b1;
+                    load8(rq, r0, r1); load8(qa, a0, a1); load8(qb, b0, b1);
+                    int ma = mismatches8(a0, a1, r0, r1), mb = mismatches8(b0, b1, r0, r1);
+                    if (jhi - jlo >= 16) {
+                        load8(rq + 8, r0, r1); load8(qa + 8, a0, a1); load8(qb + 8, b0, b1);
+                        ma += mismatches8(a0, a1, r0, r1); mb += mismatches8(b0, b1, r0, r1);
+                    }
+                    if (ma >= Mthr) { acta = false; pa = 0.0; }
+                    if (mb >= Mthr) { actb = false; pb = 0.0; }
+                }
+#endif
                 if (__any_sync(0xffffffffu, acta || actb)) {
                     const int ra = F + (ina ? xa : xlo), rb = F + (inb ? xb : (ina ? xa : xlo));
                     const bool rev = (r.packed >> 24) & FB_READ_REVERSE;
@@ -628,8 +663,8 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
                     }
                     if (lane == 0) atomicAdd(&s_lane2, (unsigned long long)steps * 64ull);
                 }
-                if (ina) W[r.wrel + ia] = acta ? pa : thrX;
-                if (inb) W[r.wrel + ib] = actb ? pb : thrX;
+                if (ina) W[r.wrel + ia] = (xa == x1) ? thrX : pa;      // the seed offset is known exactly; dropped placements keep 0
+                if (inb) W[r.wrel + ib] = (xb == x1) ? thrX : pb;
 #if FB_FUSE2
                 // the warp that completes the last unit of a read finishes the read (its products are all in W by then)
                 __threadfence_block();
@@ -1178,6 +1213,14 @@ extern "C" fb_status fb_model_upload(fb_ctx* c, const FbModel* m) {
     c->dm.e = c->d_e.p; c->dm.match = c->d_match.p; c->dm.pdf = c->d_pdf.p; c->dm.n_insert = m->n_insert;
     memcpy(c->dm.etp, m->err_type, sizeof c->dm.etp);
     c->dm.tmin = m->insert_min; c->dm.tmax = m->insert_max; c->dm.max_read_len = RL; c->dm.prunable = prunable ? 1 : 0;
+    {   // largest pass-2 mismatch factor e[k] * ETP[f][c], f != c (the kernel's table lookup, codes 0..4)
+        double emax = 0, tmax = 0;
+        for (int k = 0; k < RL; k++) emax = std::max(emax, m->err_pos[k]);
+        for (int f = 0; f < 5; f++) for (int cc = 0; cc < 5; cc++) if (f != cc) tmax = std::max(tmax, m->err_type[f * 5 + cc]);
+        const double mm = emax * tmax * (1.0 + 1e-12);
+        c->dm.mis_a = (prunable && mm > 0.0 && mm < 0.5) ? (int)std::floor(-std::log2(mm)) : 0;
+        if (c->dm.mis_a < 1) c->dm.mis_a = 0;
+    }
     // accept iff -log10(p) < cutoff (Figbird.cpp:3474,3852).  log10 is monotone, so the accepted set is
     // {p >= T}; find T = the smallest double glibc accepts, by bisection on the bit pattern.
     {
