@@ -167,18 +167,26 @@ int fillgapsMain(int argc, const char* const* argv) {
     const bool quiet = getenv("FIGBIRD_QUIET") != nullptr;
     if (!quiet) printf("Total # of gaps = %d\n", totGaps);
     Scaffolds sc;
-    if (!loadScaffolds(a.draft, sc)) { printf("Can't open contig file\n"); return 1; }
-    auto t1 = clk::now();
-    // the model is learned on its own thread while the per-gap inputs are read, encoded and uploaded; nothing before the
-    // first engine call needs it
+    // the model is learned on its own thread while the scaffolds and the per-gap inputs are read, encoded and uploaded; nothing
+    // before the first engine call needs it.  It maps myout.sam and finds the line starts first, then waits for the scaffolds
+    // (their lengths enter the statistics).
     Model model; std::string err; bool modelOk = false; double modelSecs = 0;
     std::mutex modelMu; std::condition_variable modelCv; bool modelDone = false;
+    int scState = 0;      // 0: loading, 1: loaded, -1: failed (under modelMu)
+    auto waitScaffolds = [&]() -> bool { std::unique_lock<std::mutex> l(modelMu); modelCv.wait(l, [&] { return scState != 0; }); return scState > 0; };
     std::thread modelThread([&] {
         auto m0 = clk::now();
-        bool ok = learnModel(a, sc, model, err);
+        bool ok = learnModel(a, sc, model, err, waitScaffolds);
         std::lock_guard<std::mutex> l(modelMu); modelOk = ok; modelSecs = secs(m0, clk::now()); modelDone = true; modelCv.notify_all();
     });
     struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } modelJoiner{modelThread};
+    {
+        const bool scOk = loadScaffolds(a.draft, sc);
+        { std::lock_guard<std::mutex> l(modelMu); scState = scOk ? 1 : -1; }
+        modelCv.notify_all();
+        if (!scOk) { printf("Can't open contig file\n"); return 1; }
+    }
+    auto t1 = clk::now();
     auto waitModel = [&]() -> bool { std::unique_lock<std::mutex> l(modelMu); modelCv.wait(l, [&] { return modelDone; }); return modelOk; };
     auto t2 = t1;
     if (getenv("FIGBIRD_DUMP_MODEL") && waitModel()) {

@@ -4,6 +4,7 @@
 #pragma once
 #include <cstdint>
 #include <cstdio>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -52,7 +53,8 @@ struct Model {
     long uniqueMappedReads = 0;
 };
 // returns false (message in err) when an input cannot be opened -- the caller exits 1 like the reference
-bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err);
+// waitScaffolds (optional): called once before `sc` is first read; false = the scaffolds could not be loaded
+bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err, const std::function<bool()>& waitScaffolds = nullptr);
 
 // ---- one gap line of gapInfo.txt + stat2.txt (Figbird.cpp:7359-7374)
 struct GapRecord {

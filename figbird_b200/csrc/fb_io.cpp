@@ -42,7 +42,8 @@ bool loadScaffolds(const std::string& path, Scaffolds& out) {
     }
     out.seq.push_back(cur);
     out.totalLength = 0;
-    for (auto& s : out.seq) { for (auto& ch : s) ch = (char)toupper((unsigned char)ch); out.totalLength += (long)s.size(); }
+    // toupper() of the C locale (the reference never calls setlocale), as a loop the compiler vectorises
+    for (auto& s : out.seq) { char* d = &s[0]; const size_t n = s.size(); for (size_t i = 0; i < n; i++) { const char ch = d[i]; d[i] = (ch >= 'a' && ch <= 'z') ? (char)(ch - 32) : ch; } out.totalLength += (long)n; }
     return true;
 }
 
@@ -183,6 +184,13 @@ bool writeFilledContigs(const std::string& tmpDir, const Scaffolds& sc, const st
         fprintf(out, ">%s\n", i < sc.names.size() ? sc.names[i].c_str() : "");
         buf.clear();
         for (size_t j = 0; j < s.size(); j++) {
+            if (nStart == 0 && !(gapCount >= 0 && gapCount < (int)gtf.size() && gtf[gapCount] > 0)) {
+                // a run of ordinary bases outside any gap and past the trimmed flank: copied in one piece (the last base of
+                // the scaffold and anything from the next N on take the per-character path below)
+                size_t k = j;
+                while (k + 1 < s.size() && s[k] != 'N' && s[k] != 'n') k++;
+                if (k > j) { buf.append(s, j, k - j); j = k - 1; continue; }
+            }
             bool isN = (s[j] == 'N' || s[j] == 'n');
             if (isN && nStart == 0) { nStart = 1; gapCount++; }
             if (!isN || j == s.size() - 1) {

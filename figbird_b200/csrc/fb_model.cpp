@@ -209,7 +209,7 @@ inline void fastWalkMD(const char* body, int bl, OnMis onMis) {
 
 }  // namespace
 
-bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err) {
+bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err, const std::function<bool()>& waitScaffolds) {
     // ---- stat.txt (Figbird.cpp:7084-7093)
     int maxIns = 0;
     {
@@ -297,6 +297,7 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err) 
     }
     // NB: lines keep their '\n'; tokenisers treat it as a delimiter where the reference does.
     lap("read+split");
+    if (waitScaffolds && !waitScaffolds()) { err = "Can't open contig file"; return false; }
 
     // ---- pass 1: processMapping.  The statistics are integer counts, so the file is cut into blocks that are
     // counted on separate threads and summed -- identical to the sequential result as long as every line carries its
