@@ -136,6 +136,14 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
+    # stdout carries exactly ONE JSON line: anything libraries print at the C level (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     rank, world, local = rank_info()
     os.environ["FIGBIRD_QUIET"] = "1"
     import fbcase as fc
@@ -150,7 +158,7 @@ def main():
         if rank != 0:
             return 0
         if not fc.have_reference():
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (no /root/reference at build time)"}))
+            emit({"impl": "reference", "unavailable": "oracle/_ref not built (no /root/reference at build time)"})
             return 0
         sample = prepare_case(os.path.join(base, "sample"), SAMPLE, 1102)
         # placements of the sample, counted once by our replay (needs the GPU library; outside the timed region)
@@ -169,7 +177,7 @@ def main():
                 "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "reference",
                                  "sample": "32-gap / 294 kbp sample of the c2 workload (same gap, read and coverage parameters), FillGaps partial+unmapped, as-shipped -O0 worker, numthreads=%d" % cores},
                 "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -282,7 +290,7 @@ def main():
                                 "sample": "32-gap / 294 kbp sample of the c2 workload (same parameters), FillGaps partial+unmapped, as-shipped -O0 worker, numthreads=%d, %.1f s" % (cores, secs),
                                 "steady_state": {"value": placements / steady, "seconds": steady, "note": "same sample, %d as-shipped -O0 worker processes started together (no driver sleep, no run-time compile)" % min(cores, 32)},
                                 "tuned": {"value": placements / tuned, "seconds": tuned, "note": "same, worker built -O2 -D_FORTIFY_SOURCE=0 (plain -O2 aborts, SURVEY 5)"}}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
