@@ -16,6 +16,7 @@
 #include <cstring>
 #include <algorithm>
 #include <sys/mman.h>
+#include <memory>
 #include <thread>
 #include <unistd.h>
 
@@ -302,8 +303,9 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err, 
     // ---- pass 1: processMapping.  The statistics are integer counts, so the file is cut into blocks that are
     // counted on separate threads and summed -- identical to the sequential result as long as every line carries its
     // own MD/IH tags and no insert size hits the histogram-growth corner (Figbird.cpp:203); otherwise redo it serially.
-    std::vector<LineRec> recs;
-    if (useFast) recs.resize(lines.size());      // (zero-filled pages are first touched by the thread that owns the block)
+    // (uninitialised on purpose: pass 1 visits every line and sets its record's `ok` first; pages are first touched by the
+    // thread that owns the block)
+    std::unique_ptr<LineRec[]> recs(useFast ? new LineRec[lines.size() + 1] : nullptr);
     auto pass1Line = [&](Stats& st, char* mdKeep, std::vector<char>& scratch, char* ln, bool& irregular, LineRec* rec) {
         if (rec) rec->ok = 0;
         if (ln[0] == '@') return;
@@ -594,7 +596,8 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err, 
             if (li >= lines.size()) break;
             pairs.emplace_back(i1, li++);
         }
-        std::vector<PairRes> res(pairs.size());
+        const size_t nPairs = pairs.size();
+        std::unique_ptr<PairRes[]> res(new PairRes[nPairs + 1]);      // (uninitialised: every element is written by its thread)
         std::vector<std::thread> th;
         for (int t = 0; t < nThreads; t++) th.emplace_back([&, t] {
             char md1[1000], md2[1000]; md1[0] = md2[0] = 0;
@@ -624,8 +627,8 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err, 
         // unless one of the group's names is "*" (the initial state of the reference's loop); the last group never is.  Groups are
         // independent, so every thread takes the groups that start in its block (it may read past the block's end).
         auto same = [](const char* a, int an, const char* b, int bn) { return an == bn && memcmp(a, b, an) == 0; };
-        std::vector<uint32_t> okIdx; okIdx.reserve(res.size());
-        for (size_t i = 0; i < res.size(); i++) if (res[i].ok) okIdx.push_back((uint32_t)i);
+        std::vector<uint32_t> okIdx; okIdx.reserve(nPairs);
+        for (size_t i = 0; i < nPairs; i++) if (res[i].ok) okIdx.push_back((uint32_t)i);
         const size_t M = okIdx.size();
         std::vector<std::vector<long>> hist(nThreads, std::vector<long>(1000 + 16, 0));
         th.clear();
