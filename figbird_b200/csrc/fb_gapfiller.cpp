@@ -500,7 +500,7 @@ double GapFill::unmappedEpilogue(const ItemResult& r, int slot, int Lg, int fina
     for (int q = 0; q < R; q++) {
         markAccepted_[q] = 0; finalReadpos_[q] = Pos3{-200, 0, -1};
         if (Lg == og_) unmPosOrg_[q] = Pos3{-200, 0, 0};
-        mlvNonZero_[q] = (p1[q] > 0) ? (log10(p1[q]) != 0) : 0;
+        mlvNonZero_[q] = (p1[q] > 0) ? (p1[q] != 1.0) : 0;      // log10(p) != 0: only p == 1 has a zero logarithm (|log10(1 +- ulp)| > 4e-17)
     }
     for (int q = 0; q < R; q++) {
         const double maxProb = p2[q] >= 0 ? p2[q] : -DBL_MAX;
