@@ -56,7 +56,8 @@ size_t cstrlen(const std::vector<char>& b) { return strnlen(b.data(), b.size());
 }  // namespace
 
 GapFill::GapFill(const Args& a, const Model& m, const Scaffolds& sc, GapInput&& in) : a_(a), m_(m), sc_(sc), in_(std::move(in)) {
-    memset(pileStr_, 0, sizeof pileStr_);
+    memset(ovl_, 0, sizeof ovl_);
+    savedTemp_[0] = savedTemp_[1] = savedFinal_[0] = savedFinal_[1] = -1; sideLimit_ = 30;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -331,13 +332,32 @@ void GapFill::pileUp(int Lg, bool makeStrings) {
         for (int k = 0; k < 4; k++) if (cnt[i][k] > maxVal) { maxVal = (int)cnt[i][k]; maxIndex = k; }
         if (i <= leftMax - 5 || i >= rightMin + 5) {
             char ch = maxIndex == 0 ? 'A' : maxIndex == 1 ? 'C' : maxIndex == 2 ? 'G' : 'T';
-            if (i <= leftMax - 5) { if (lc < 199) pl[lc] = ch; lc++; }
-            else { if (rc < 99) pr[rc] = ch; rc++; }
+            if (i <= leftMax - 5) { if (lc < kOvlBytes) pl[lc] = ch; lc++; }
+            else { if (100 + rc < kOvlBytes) pr[rc] = ch; rc++; }
         }
     }
-    if (lc < 200) pl[lc] = '\0';
-    if (rc < 100) pr[rc] = '\0';
-    pileStr_[199] = '\0';
+    if (lc < kOvlBytes) pl[lc] = '\0';
+    if (100 + rc < kOvlBytes) pr[rc] = '\0';
+}
+
+// initialize(gapEstimate) runs update_partial_prob for every evaluated length (Figbird.cpp:2111-2115).  The gap rows it
+// produces are computed on the device; on the host only its overflow matters: partial_right holds min(longest right-side
+// pile-up, Lg) - 5 characters, and from 100 on they land on the saved-read indices and side_limit (see ovl_).  Reads of up
+// to ~105 bases can never get there, so the strings are only rebuilt for the (gap, length) pairs that can.
+void GapFill::initializeEffects(int Lg) {
+    if (maxRightCi_ < 0) {
+        maxRightCi_ = 0;
+        const int np = (int)std::min<size_t>(in_.partial.size(), 3001);
+        for (int p = 0; p < np; p++) {
+            const PartialRead& pr = in_.partial[p];
+            if (!(pr.match == 2 || pr.match == 3)) continue;
+            int ci = pr.clippedIndex;
+            if (repeatflag_[p][0] == 1) ci = repeatflag_[p][2] + repeatflag_[p][1] - 1;
+            if (repeatflag_[p][0] == 2) ci = repeatflag_[p][1];
+            maxRightCi_ = std::max(maxRightCi_, ci);
+        }
+    }
+    if (std::min(maxRightCi_, Lg) - 5 >= 100) pileUp(Lg, true);
 }
 
 void GapFill::setConcensus(const std::vector<uint8_t>& codes, int len) {
@@ -480,7 +500,7 @@ void GapFill::borderUpdate(int Lg) {
     }
     // fall back to the partial pile-up string on the left (the right-hand twin can never fire: its
     // match counter starts at 1, Figbird.cpp:4040,4321)
-    const int plen = (int)strlen(pileStr_);
+    const int plen = (int)strnlen(pileStr_, kOvlBytes);      // strlen(partial_left): may run on into what follows it
     if (flag1 == 1 && numMatch0 == 0 && indexPair[0] < plen)
         for (int f = indexPair[0] + 1; f < plen; f++) { int cd = code(pileStr_[f]); if (f >= 0 && f < Lg && cd < 4) countPos[f][cd] += 1; }
     for (int j = 0; j < Lg; j++) {
@@ -663,6 +683,7 @@ double GapFill::partialEpilogue(const ItemResult& r, int slot, int Lg) {
 double GapFill::evalCandidate(const ItemResult& r, int Lg, int finalizeFlag) {
     double like = 0;
     refPlacements_ += r.placements;
+    initializeEffects(Lg);
     if (prep_.mode == FB_MODE_PARTIAL) {
         for (int s = 0; s < r.calls; s++) { validCount_ = 0; like = partialEpilogue(r, s, Lg); }
     } else {
@@ -1109,6 +1130,7 @@ GapResult GapFill::run(DeviceQueue& dev, int batchGapIndex) {
             if (unmapped && !finalizeFlag) {
                 // EM rounds ran with finalize_flag=0; the extra pass is the call with finalize_flag=1 (Figbird.cpp:6348-6352)
                 validCount_ = 0; refPlacements_ += r.placements;
+                initializeEffects(gapEstimate);
                 likelihood = unmappedEpilogue(r, 0, gapEstimate, 1, 0, r.calls - 1);
             } else likelihood = evalCandidate(r, gapEstimate, finalizeFlag);
             lastSoft_ = r.soft;

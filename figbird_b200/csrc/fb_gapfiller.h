@@ -70,7 +70,6 @@ private:
     int og_ = 0, unmReadLen_ = 0, partialReadLen_ = 0, midLimitP_ = 0, midLimitU_ = 0, negOverlap_ = 0;
     int largeGapFlag_ = 0, allocArg_ = 0, fillflag_ = 1;
     float frac1_ = 1, frac2_ = 1;
-    int sideLimit_ = 30;
     std::string gapLeft_, gapRight_;
     int partialReadCount_ = 0, numReads_ = 0;
     std::vector<std::array<int, 3>> repeatflag_;
@@ -81,7 +80,6 @@ private:
     std::vector<char> mlvNonZero_;
     std::vector<Pos3> finalReadpos_, unmPosOrg_;
     std::vector<std::array<int, 3>> partialPosOrg_;
-    int savedTemp_[2] = {-1, -1}, savedFinal_[2] = {-1, -1};
     int umaxFlags_ = 0;
     int gapLength_ = 0;                     // this->gapLength
     std::vector<char> concensus_, bestString_, originalStr_;   // C buffers with strcpy semantics
@@ -89,7 +87,17 @@ private:
     std::vector<std::array<double, 5>> counts_;   // countsGap gap rows (host copy, finalize / border update)
     std::vector<std::array<double, 5>> qualGap_;
     std::vector<std::vector<double>> partialQuality_;
-    char pileStr_[200];                     // partial_left[100] followed by partial_right[100]
+    // The reference keeps `char partial_left[100], partial_right[100]; int partial_saved_read_temp[2], partial_saved_read_final[2];
+    // int side_limit;` side by side (Figbird.cpp:1625-1627) and update_partial_prob writes the pile-up strings without a bound
+    // (:2063-2084): with reads longer than ~105 bases partial_left runs into partial_right and partial_right into the saved-read
+    // indices and side_limit, which finalize() then reads (:5345).  The layout of the x86-64 build is reproduced byte for byte
+    // so that those reads see what the reference's see; writes past side_limit (pointers in the reference) are dropped.
+    alignas(8) unsigned char ovl_[224];
+    char* const pileStr_ = (char*)ovl_;                       // [0,100) partial_left, [100,200) partial_right
+    int32_t* const savedTemp_ = (int32_t*)(ovl_ + 200);      // partial_saved_read_temp[2]
+    int32_t* const savedFinal_ = (int32_t*)(ovl_ + 208);     // partial_saved_read_final[2]
+    int32_t& sideLimit_ = *(int32_t*)(ovl_ + 216);           // side_limit
+    static constexpr int kOvlBytes = 220;
     int overlapThreshold_ = 5;
     std::string draw_;
     std::vector<uint8_t> lastSoft_;         // computeSequence(0,0) of the most recent placeReads call
@@ -104,6 +112,8 @@ private:
     int findRepeat();
     int findContigMatch() const;
     void pileUp(int Lg, bool makeStrings);
+    void initializeEffects(int Lg);     // what initialize() leaves behind on the host besides the gap rows (see ovl_)
+    int maxRightCi_ = -1;               // longest right-side pile-up of the gap (-1: not computed yet)
     void setConcensus(const std::vector<uint8_t>& codes, int len);
     void copyStr(std::vector<char>& dst, const std::vector<char>& src);
     ItemSpec emSpec(int Lg) const;

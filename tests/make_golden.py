@@ -29,6 +29,9 @@ CASES = {
     # BASELINE configs[3] read parameters
     "g5": dict(gen={"genome": 60000, "gaplist": "1200,2500,800", "seed": 51, "cov": 30, "sd": 50}, readlen=150, insert=500),
     # BASELINE configs[4] regime: gaps of several kbp under the 3500 bp jump library
+    # 150-base reads with right-side pile-ups of more than 105 bases: update_partial_prob overruns partial_right into the
+    # saved-read indices that finalize() reads (Figbird.cpp:1625-1627, 2063-2084, 5345); the host reproduces that layout
+    "g7": dict(gen={"genome": 45000, "gaplist": "150,230,118", "seed": 58, "cov": 40, "sd": 50, "readN": 10}, readlen=150, insert=500),
     "g6": dict(gen={"genome": 90000, "gaplist": "5000,3000,1500", "seed": 52, "cov": 20, "sd": 350}, readlen=100, insert=3500),
 }
 
