@@ -34,8 +34,8 @@ def main():
             t0 = time.time(); r = fc.run_reference(case, mode, threads=os.cpu_count() or 1, worker="figbird_worker_O2"); t1 = time.time()
             o = fc.run_ours(case, mode, fc.product_exe(), threads=os.cpu_count() or 1); t2 = time.time()
             ok = {f: r[f] == o[f] for f in ("gapout.txt", "filledContigs.fa", "Ncount.txt")}
-            a, b = fc.draw_by_gap(r["draw.txt"]), fc.draw_by_gap(o["draw.txt"])
-            ok["draw"] = sorted(a) == sorted(b) and all(a[k].rstrip(b"\n") == b[k].rstrip(b"\n") for k in a)
+            # the reference concatenates draw.txt in worker order (and some gaps write lines without a header): compare as multisets of lines
+            ok["draw"] = sorted((r["draw.txt"] or b"").split(b"\n")) == sorted((o["draw.txt"] or b"").split(b"\n"))
             bad += sum(1 for v in ok.values() if not v)
             print(name, mode, ok, "reference %.1f s, product %.1f s" % (t1 - t0, t2 - t1), flush=True)
     print("MISMATCHES" if bad else "ALL IDENTICAL")
