@@ -46,7 +46,16 @@ def test_oracle_matches_reference_outputs(case, mode):
     assert worst <= 1e-9, "countsGap relative error %g" % worst
 
 
+LIGHT = ("g1", "g2", "g4")      # the host-logic tests below repeat whole runs: small fixtures keep the CPU suite to a few minutes
+
+
+def _light(case):
+    if os.path.basename(case) not in LIGHT:
+        pytest.skip("host-logic test runs on the small fixtures only")
+
+
 def test_sharding_over_two_contexts_is_invariant(case):
+    _light(case)
     """N>1 host path on CPU: two engine contexts (FIGBIRD_GPUS=0,1), gaps sharded cost-balanced, same files out."""
     one = fc.run_ours(case, "unmapped", fc.oracle_exe(), name="one")
     two = fc.run_ours(case, "unmapped", fc.oracle_exe(), extra_env={"FIGBIRD_GPUS": "0,1", "FIGBIRD_INFLIGHT": "2"}, name="two")
@@ -58,6 +67,7 @@ def test_sharding_over_two_contexts_is_invariant(case):
 def test_threaded_model_learning_is_identical(case, mode):
     """learnModel cut into blocks on host threads (forced small blocks) gives the same tables and cut-offs as the
     sequential parse, i.e. as the reference (Figbird.cpp:7118-7200)."""
+    _light(case)
     model = os.path.join(case, "oracle_model_thr_%s.txt" % mode)
     o = fc.run_ours(case, mode, fc.oracle_exe(), extra_env={"FIGBIRD_DUMP_MODEL": model, "FIGBIRD_HOST_THREADS": "5", "FIGBIRD_MODEL_BLOCK": "64"}, name="thr")
     exp = gu.expected(case, mode)
