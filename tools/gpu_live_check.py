@@ -15,6 +15,7 @@ CASES = {
     "L4": ({"genome": 120000, "gaps": 14, "gapmin": 10, "gapmax": 1000, "seed": 54, "cov": 40, "sd": 50, "negfrac": 0.3, "readN": 40}, 150, 500),
     "L5": ({"genome": 100000, "gaps": 10, "gapmin": 400, "gapmax": 700, "seed": 55, "cov": 50, "sd": 20}, 100, 200),
     "L6": ({"genome": 400000, "gaps": 8, "gapmin": 50, "gapmax": 3000, "seed": 56, "cov": 20, "sd": 350}, 100, 3500),
+    "L8": ({"genome": 700000, "gaps": 100, "gapmin": 10, "gapmax": 2000, "seed": 61, "cov": 40, "sd": 50, "negfrac": 0.05, "readN": 200}, 150, 500),
     "L7": ({"genome": 400000, "gaps": 60, "gapmin": 10, "gapmax": 2000, "seed": 57, "cov": 40, "sd": 50, "negfrac": 0.05}, 150, 500),
 }
 
