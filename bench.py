@@ -267,6 +267,8 @@ def main():
                                         "note": "flank terms come from the per-gap cache and pass 2 is pruned, so the kernel walks fewer terms than the reference evaluates"},
             "smem": {"achieved_gbs": 16.0 * lane1 / (dev_ms * 1e-3) / 1e9, "peak_gbs": smem_peak, "frac": 16.0 * lane1 / (dev_ms * 1e-3) / 1e9 / smem_peak,
                      "note": "pass-1 walk only: 16 B (LDS.128 of {P, E-P}) per executed gap-row lane step / kernel time, against 128 B/clk/SM x SMs x SM clock"},
+            "issue": ({"achieved": dom.get("issue_active_pct"), "peak": 100.0, "unit": "% of issue slots active (ncu sm__issue_active, dominant launch of the committed capture)",
+                       "frac": (dom.get("issue_active_pct") or 0.0) / 100.0} if dom else None),
             "ncu": {k: dom.get(k) for k in ("issue_active_pct", "smem_wavefronts_pct", "fp64_pipe_pct", "alu_pipe_pct", "lsu_pipe_pct", "warps_active_pct", "stall_barrier")} if dom else None,
             "hbm": {"achieved_gbs": (h2d + d2h) / (dev_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                     "note": "algorithmic HBM bytes ~= result arena + inputs; tables live in shared memory"}}
