@@ -35,6 +35,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 WORKLOADS = {
     # name: (fbgen args, readlen, insert)
     "c2": ({"genome": 4600000, "scaffolds": 10, "gaps": 500, "gapmin": 10, "gapmax": 500, "cov": 50, "sd": 20, "near": 700, "model-pairs": 300000}, 100, 200),
+    # BASELINE configs[3] read / gap parameters (2x150 bp @ 500 bp, gaps 10-2000 bp, 40x) at single-GPU size: not the headline, a
+    # second operating point (150-base reads, candidates whose tables live in global memory, large-gap rounds)
+    "c4s": ({"genome": 5000000, "scaffolds": 10, "gaps": 500, "gapmin": 10, "gapmax": 2000, "cov": 40, "sd": 50, "near": 1500, "model-pairs": 300000}, 150, 500),
     "c1": ({"genome": 1000000, "scaffolds": 4, "gaps": 50, "gapmin": 10, "gapmax": 500, "cov": 30, "sd": 20, "near": 700, "model-pairs": 150000}, 100, 200),
     "tiny": ({"genome": 80000, "scaffolds": 1, "gaps": 8, "gapmin": 5, "gapmax": 300, "cov": 30, "sd": 20}, 100, 200),
 }
