@@ -4,8 +4,8 @@
 // processes it spawns (Figbird.cpp main :6909-7508).  What is different by design:
 //   * no worker processes, no run-time compilation: the model is learned once, gaps are sharded
 //     cost-balanced over the visible GPUs (FIGBIRD_GPUS), one engine context per GPU, no collective;
-//   * every gap runs its sequential control logic on a host thread; the device requests of all gaps in
-//     flight on a GPU are merged into one fb_em_run per tick (BatchQueue below);
+//   * every gap runs its sequential control logic on a fiber of a small worker pool; the device requests of all
+//     gaps in flight on a lane are merged into one fb_em_run per tick (LaneQueue below);
 //   * draw.txt is written in gap order (the reference concatenates it in worker order, FillGaps.cpp:222-258).
 #include <algorithm>
 #include <atomic>
@@ -18,30 +18,48 @@
 #include <stdexcept>
 #include <thread>
 #include <time.h>
+#include <sys/mman.h>
+#include <ucontext.h>
 
 #include "fb_gapfiller.h"
 #include "fb_io.h"
 
 namespace fb {
 
-// Merges the requests of all gap threads that are currently blocked into one engine call.  The last
-// thread to block (or to leave) runs the flush; nobody else is runnable at that moment.
-class BatchQueue : public DeviceQueue {
+// ---------------------------------------------------------------------------------------------------------
+// Lane scheduler.  A lane = one engine context + a few worker threads.  Every gap runs the reference's
+// *sequential* control (GapFill::run) on its own fiber (ucontext, 256 KB stack): a device request parks the
+// fiber instead of blocking an OS thread, so thousands of gaps can be in flight on a handful of threads.
+// A worker owns its fibers for their whole life (no migration).  When all of a worker's fibers are parked it
+// hands their requests to the lane; the last worker to arrive flushes them as ONE fb_em_run, after which every
+// worker resumes its fibers and each fiber unpacks its own results from the pinned arena (which stays valid
+// until the next flush, and that needs every worker to arrive again).
+// ---------------------------------------------------------------------------------------------------------
+struct Fiber {
+    ucontext_t ctx, *ret = nullptr;
+    void* stack = nullptr; size_t stackBytes = 0;
+    GapFill* fill = nullptr; int bidx = 0, gap = 0;
+    DeviceQueue* dev = nullptr;
+    GapResult result; std::string error;
+    const std::vector<ItemSpec>* reqItems = nullptr;
+    std::vector<const FbItemOut*> outs;
+    bool done = false, failed = false;
+};
+static thread_local Fiber* tlsFiber = nullptr;
+
+class LaneQueue : public DeviceQueue {
 public:
-    BatchQueue(fb_ctx* ctx, int workers) : ctx_(ctx), running_(workers) {}
-    void submit(int gapIdx, const std::vector<ItemSpec>& items, std::vector<ItemResult>& results) override {
-        Req rq{gapIdx, &items, {}, false};
-        {
-            std::unique_lock<std::mutex> lk(mu_);
-            reqs_.push_back(&rq);
-            if ((int)reqs_.size() >= running_) flush(lk);
-            else cv_.wait(lk, [&] { return rq.done; });
-            if (failed_) throw std::runtime_error(err_);
-        }
-        // every gap thread unpacks its own results (the arena stays valid until the next flush, which needs this thread to block again)
-        results.clear(); results.reserve(rq.outs.size());
-        for (const FbItemOut* h : rq.outs) {
-            ItemResult res; const unsigned char* b = (const unsigned char*)h;
+    LaneQueue(fb_ctx* ctx, int workers) : ctx_(ctx), running_(workers) {}
+    // called on a fiber: park until the lane has run the request
+    void submit(int, const std::vector<ItemSpec>& items, std::vector<ItemResult>& results) override {
+        Fiber* f = tlsFiber;
+        f->reqItems = &items; f->outs.clear();
+        swapcontext(&f->ctx, f->ret);
+        if (f->failed) throw std::runtime_error(err_);
+        results.clear(); results.reserve(f->outs.size());
+        for (const FbItemOut* h : f->outs) {
+            results.emplace_back();
+            ItemResult& res = results.back(); const unsigned char* b = (const unsigned char*)h;
             res.calls = h->calls; res.compCount = h->comp_count; res.flags = h->flags; res.nReads = h->n_reads;
             res.candLen = h->cand_len; res.nSlots = h->n_slots; res.placements = h->placements;
             const size_t n = (size_t)h->n_slots * h->n_reads;
@@ -52,54 +70,121 @@ public:
             res.hard.assign(b + h->off_hard, b + h->off_hard + h->cand_len);
             const int32_t* cv = (const int32_t*)(b + h->off_cov); res.cov.assign(cv, cv + h->cand_len);
             if (h->off_counts >= 0) { const double* c = (const double*)(b + h->off_counts); res.counts.assign(c, c + (size_t)5 * h->cand_len); }
-            results.push_back(std::move(res));
         }
+        f->reqItems = nullptr;
+    }
+    // called by a worker thread whose fibers are all parked: returns when their requests have been run
+    void exchange(const std::vector<Fiber*>& parked) {
+        std::unique_lock<std::mutex> lk(mu_);
+        for (Fiber* f : parked) reqs_.push_back(f);
+        arrived_++;
+        if (arrived_ >= running_) flush(lk);
+        else { const int64_t gen = gen_; cv_.wait(lk, [&] { return gen_ != gen; }); }
     }
     void workerExit() {
         std::unique_lock<std::mutex> lk(mu_);
         running_--;
-        if (!reqs_.empty() && (int)reqs_.size() >= running_) flush(lk);
+        if (running_ > 0 && arrived_ >= running_) flush(lk);
     }
     int64_t ticks() const { return ticks_; }
     double engineSeconds() const { return tEngine_; }
-    double copySeconds() const { return tCopy_; }
 
 private:
-    struct Req { int gap; const std::vector<ItemSpec>* items; std::vector<const FbItemOut*> outs; bool done; };
     void flush(std::unique_lock<std::mutex>&) {
-        std::vector<Req*> batch; batch.swap(reqs_);
+        std::vector<Fiber*> batch; batch.swap(reqs_);
+        arrived_ = 0;
         std::vector<FbWorkItem> wi;
-        for (Req* r : batch) for (const ItemSpec& s : *r->items) {
-            FbWorkItem w{}; w.kind = s.kind; w.gap = r->gap; w.cand_len = s.candLen; w.max_rounds = s.maxRounds; w.flags = s.flags;
+        for (Fiber* f : batch) for (const ItemSpec& s : *f->reqItems) {
+            FbWorkItem w{}; w.kind = s.kind; w.gap = f->bidx; w.cand_len = s.candLen; w.max_rounds = s.maxRounds; w.flags = s.flags;
             w.comp_count_in = s.compIn; w.counts_in = s.countsIn.empty() ? nullptr : s.countsIn.data();
             w.string_in = s.stringIn.empty() ? nullptr : s.stringIn.data();
             wi.push_back(w);
         }
-        std::vector<const FbItemOut*> outs(wi.size(), nullptr);
+        outs_.assign(wi.size(), nullptr);
         auto c0 = std::chrono::steady_clock::now();
-        fb_status st = wi.empty() ? FB_OK : fb_em_run(ctx_, wi.data(), (int32_t)wi.size(), outs.data());
-        auto c1 = std::chrono::steady_clock::now();
-        tEngine_ += std::chrono::duration<double>(c1 - c0).count();
+        fb_status st = (wi.empty() || failed_) ? FB_OK : fb_em_run(ctx_, wi.data(), (int32_t)wi.size(), outs_.data());
+        tEngine_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - c0).count();
         ticks_++;
         if (st != FB_OK) { failed_ = true; err_ = std::string("fb_em_run failed: ") + fb_last_error(ctx_); }
         size_t k = 0;
-        for (Req* r : batch) {
-            r->outs.clear();
-            if (!failed_) r->outs.assign(outs.begin() + k, outs.begin() + k + r->items->size());
-            k += r->items->size();
-            r->done = true;
+        for (Fiber* f : batch) {
+            const size_t n = f->reqItems->size();
+            f->failed = failed_;
+            if (!failed_) f->outs.assign(outs_.begin() + k, outs_.begin() + k + n);
+            k += n;
         }
-        tCopy_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - c1).count();
+        gen_++;
         cv_.notify_all();
     }
     fb_ctx* ctx_;
     std::mutex mu_; std::condition_variable cv_;
-    std::vector<Req*> reqs_;
-    int running_;
+    std::vector<Fiber*> reqs_;
+    std::vector<const FbItemOut*> outs_;
+    int running_, arrived_ = 0;
+    int64_t gen_ = 0;
     bool failed_ = false; std::string err_;
     int64_t ticks_ = 0;
-    double tEngine_ = 0, tCopy_ = 0;
+    double tEngine_ = 0;
 };
+
+static void fiberEntry(unsigned lo, unsigned hi) {
+    Fiber* f = (Fiber*)(((uintptr_t)hi << 32) | (uintptr_t)lo);
+    try { f->result = f->fill->run(*f->dev, f->bidx); }
+    catch (const std::exception& e) { f->error = e.what(); if (f->error.empty()) f->error = "gap worker failed"; }
+    catch (...) { f->error = "gap worker failed"; }
+    f->done = true;
+    // returning switches to uc_link (the worker's context)
+}
+
+// One worker thread of a lane: keeps up to `cap` gaps in flight on fibers, taking gaps from the lane's list.
+struct LaneWork {
+    const std::vector<int>* mine = nullptr;
+    std::vector<std::unique_ptr<GapFill>>* fills = nullptr;
+    std::vector<GapResult>* results = nullptr;
+    std::atomic<int> next{0};
+    std::mutex emu; std::string error;
+};
+static void laneWorker(LaneQueue& q, LaneWork& lw, int cap) {
+    constexpr size_t kStack = 256 * 1024;
+    ucontext_t self;
+    std::vector<Fiber*> active, parked;
+    std::vector<void*> freeStacks;
+    auto resume = [&](Fiber* f) { tlsFiber = f; f->ret = &self; swapcontext(&self, &f->ctx); tlsFiber = nullptr; };
+    auto retire = [&](Fiber* f) {
+        if (!f->error.empty()) { std::lock_guard<std::mutex> l(lw.emu); if (lw.error.empty()) lw.error = f->error; }
+        else (*lw.results)[f->gap] = std::move(f->result);
+        freeStacks.push_back(f->stack);
+        delete f;
+    };
+    auto topUp = [&]() {
+        while ((int)active.size() < cap) {
+            const int i = lw.next++;
+            if (i >= (int)lw.mine->size()) break;
+            Fiber* f = new Fiber();
+            f->gap = (*lw.mine)[i]; f->bidx = i; f->fill = (*lw.fills)[f->gap].get(); f->dev = &q;
+            if (!freeStacks.empty()) { f->stack = freeStacks.back(); freeStacks.pop_back(); }
+            else f->stack = mmap(nullptr, kStack, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_STACK, -1, 0);
+            if (f->stack == MAP_FAILED) { f->stack = nullptr; f->error = "cannot allocate a fiber stack"; std::lock_guard<std::mutex> l(lw.emu); if (lw.error.empty()) lw.error = f->error; delete f; break; }
+            f->stackBytes = kStack;
+            getcontext(&f->ctx);
+            f->ctx.uc_stack.ss_sp = f->stack; f->ctx.uc_stack.ss_size = kStack; f->ctx.uc_link = &self;
+            const uintptr_t p = (uintptr_t)f;
+            makecontext(&f->ctx, (void (*)())fiberEntry, 2, (unsigned)(p & 0xffffffffu), (unsigned)(p >> 32));
+            resume(f);
+            if (f->done) retire(f); else active.push_back(f);
+        }
+    };
+    topUp();
+    while (!active.empty()) {
+        q.exchange(active);
+        parked.swap(active); active.clear();
+        for (Fiber* f : parked) { resume(f); if (f->done) retire(f); else active.push_back(f); }
+        parked.clear();
+        topUp();
+    }
+    for (void* s : freeStacks) munmap(s, kStack);
+    q.workerExit();
+}
 
 static bool parseArgs(int argc, const char* const* argv, Args& a) {
     if (argc < 16) return false;
@@ -219,6 +304,7 @@ int fillgapsMain(int argc, const char* const* argv) {
     // ---- shard gaps over GPUs: longest-processing-time-first on the cost estimate
     std::vector<int> devs = visibleDevices();
     const int nD = (int)devs.size();
+    int nGpus = 0; { std::vector<int> u(devs); std::sort(u.begin(), u.end()); nGpus = (int)(std::unique(u.begin(), u.end()) - u.begin()); }
     std::vector<std::vector<int>> shard(nD);
     {
         std::vector<int> order(nG); for (int i = 0; i < nG; i++) order[i] = i;
@@ -281,22 +367,24 @@ int fillgapsMain(int argc, const char* const* argv) {
 
         auto d1 = clk::now();
         devCtx[d] = secs(d0, d1);
-        int inflight = 512;
+        int inflight = 1024;
         if (const char* e = getenv("FIGBIRD_INFLIGHT")) inflight = std::max(1, atoi(e));
-        const int workers = std::max(1, std::min((int)mine.size(), inflight));
-        BatchQueue q(ctx, workers);
-        std::atomic<int> next(0);
+        // worker threads of this lane: the lanes of one GPU alternate (one waits for its kernels while the other replays), so
+        // every lane may use the host threads of its GPU
+        int nWorkers = std::max(1, hostThreads / std::max(1, nGpus));
+        if (const char* e = getenv("FIGBIRD_LANE_WORKERS")) nWorkers = std::max(1, atoi(e));
+        nWorkers = std::max(1, std::min(nWorkers, (int)mine.size()));
+        const int cap = std::max(1, (std::min((int)mine.size(), inflight) + nWorkers - 1) / nWorkers);
+        LaneQueue q(ctx, nWorkers);
+        LaneWork lw; lw.mine = &mine; lw.fills = &fills; lw.results = &results;
         std::vector<std::thread> th;
-        std::mutex emu;
         std::atomic<long long> cpuNs(0);
-        for (int w = 0; w < workers; w++) th.emplace_back([&] {
-            try {
-                for (int i; (i = next++) < (int)mine.size();) { int g = mine[i]; results[g] = fills[g]->run(q, i); }
-            } catch (const std::exception& e) { std::lock_guard<std::mutex> l(emu); devErr[d] = e.what(); }
-            { timespec ts; clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts); cpuNs += (long long)ts.tv_sec * 1000000000LL + ts.tv_nsec; }
-            q.workerExit();
+        for (int w = 0; w < nWorkers; w++) th.emplace_back([&] {
+            laneWorker(q, lw, cap);
+            timespec ts; clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts); cpuNs += (long long)ts.tv_sec * 1000000000LL + ts.tv_nsec;
         });
         for (auto& t : th) t.join();
+        if (!lw.error.empty()) devErr[d] = lw.error;
         devWork[d] = secs(d1, clk::now()); devCpu[d] = cpuNs.load() * 1e-9;
         {   // this run's share of the context's cumulative counters
             FbCounters c1{}; fb_get_counters(ctx, &c1);
@@ -305,7 +393,7 @@ int fillgapsMain(int argc, const char* const* argv) {
             c1.device_union_ms -= ctr0.device_union_ms;
             devCtr[d] = c1;
         }
-        devTicks[d] = q.ticks(); devEng[d] = q.engineSeconds(); devCopy[d] = q.copySeconds();
+        devTicks[d] = q.ticks(); devEng[d] = q.engineSeconds();
         releaseCtx(devs[d], laneOf, ctx);
     });
     for (auto& t : devThreads) t.join();
