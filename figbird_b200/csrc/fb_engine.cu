@@ -410,6 +410,8 @@ __global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(co
             if (it.string_in_off >= 0) { const unsigned char* sin = prm.in_arena + it.string_in_off; for (int x = tid; x < Lg; x += kThreads) PREV[x] = sin[x]; prevValid = 1; }
             comp = it.comp_in;
         } else {
+            // previous_str carried in from an earlier run() of the same length (Figbird.cpp:3919-3927): seeds comp_count's comparison
+            if (it.string_in_off >= 0) { const unsigned char* sin = prm.in_arena + it.string_in_off; for (int x = tid; x < Lg; x += kThreads) PREV[x] = sin[x]; prevValid = 1; }
             // gap rows from the partial pile-ups (update_partial_prob, Figbird.cpp:2039-2081)
             const int* plp = prm.pile_l + 4 * (size_t)g.pile_begin; const int* prp = prm.pile_r + 4 * (size_t)g.pile_begin;
             for (int x = tid; x < Lg; x += kThreads) {

@@ -5,9 +5,9 @@
 // the engine (include/figbird_b200.h); this file holds only the sequential decision logic of the reference
 // worker, re-expressed over device results.  It has to reproduce the reference's discrete decisions exactly
 // (the filled sequence is compared byte for byte), so thresholds, tie rules and even benign quirks follow
-// GapFiller (Figbird.cpp:1563-6684) -- cited per function.  Window geometry (left/right_maxDistance) is not
-// modelled: inside the supported domain (the +-readLength rows around the gap lie inside the scaffold)
-// the reference's results do not depend on it.
+// GapFiller (Figbird.cpp:1563-6684) -- cited per function.  Window geometry (left/right_maxDistance and their clipping
+// at scaffold ends) is not modelled: inside the supported domain (the +-readLength rows around the gap lie inside the
+// scaffold, see prepare()) the reference's results do not depend on it.
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -130,8 +130,16 @@ void GapFill::prepare() {
     // largest candidate ever evaluated: gapMax, the checkGapReads probes (<=3*og or 70) and og itself
     int gapMaxEver = std::max(og_, (int)((float)og_ * frac2_));
     if (a_.unmapped == 1 && og_ <= midLimitU_) gapMaxEver = std::max(gapMaxEver, og_ < 30 ? 70 : 3 * og_);
+    // Supported domain = where the reference's own result is defined.  Its window is clipped at the scaffold ends
+    // (initialize_start_end, Figbird.cpp:2268-2296): left_maxDistance = min(maxDistance, gapStart), right_maxDistance =
+    // min(maxDistance, scaffold end - gapStart - Lg).  Pass 1 skips window rows < 0 (:3157,3578) but pass 2 indexes gapString
+    // unguarded (:3386,3767,5036), and no loop bounds the row index above, so a read base outside the window reads memory the
+    // worker never initialised.  With gapStart >= read length - 1 and (scaffold end - gapStart - Lg) >= read length - 1 for every
+    // evaluated Lg no read base leaves the window and the clip changes nothing that is scored: the gap is filled exactly as the
+    // reference fills it (goldens g8 / g9).  Outside that (a gap within a read length of a scaffold end) the reference's output
+    // depends on heap contents; such gaps are emitted unfilled.  side_limit = min(30, left_maxDistance) stays 30 here.
     prep_.supported = r.contigNo >= 0 && r.contigNo < (int)sc_.seq.size() && r.gapStart >= F && a_.maxDistance >= F - 1 &&
-                      r.gapStart + og_ + F <= clen && r.gapStart + gapMaxEver + F <= clen && r.gapStart - a_.maxDistance >= 0;
+                      r.gapStart + og_ + F <= clen && r.gapStart + gapMaxEver + F <= clen;
     if (!prep_.supported) { prep_.attempt = false; return; }
     prep_.flank.resize(2 * F);
     for (int i = 0; i < F; i++) prep_.flank[i] = code(ctg[r.gapStart - F + i]);
@@ -298,32 +306,45 @@ int GapFill::findContigMatch() const {
 // The string side of update_partial_prob (Figbird.cpp:2036-2084): majority strings inside the pile-up edges.
 void GapFill::pileUp(int Lg, bool makeStrings) {
     if (!makeStrings) return;
-    int leftMax = -kMaxGap, rightMin = kMaxGap;
-    const int np = (int)std::min<size_t>(in_.partial.size(), 3001);
-    std::vector<std::array<double, 4>> cnt(Lg, std::array<double, 4>{{1, 1, 1, 1}});
-    for (int p = 0; p < np; p++) {
-        const PartialRead& pr = in_.partial[p];
-        const int len = (int)pr.seq.size();
-        int ci = pr.clippedIndex;
-        if (repeatflag_[p][0] == 1) ci = repeatflag_[p][2] + repeatflag_[p][1] - 1;
-        if (repeatflag_[p][0] == 2) ci = repeatflag_[p][1];
-        int stop1 = std::min(len - ci - 1, Lg);
-        int stop2 = ci <= Lg ? 0 : ci - Lg;
-        if (pr.match == 1 || pr.match == 4) {
-            int j = 0;
-            for (int i = ci + 1; i < ci + 1 + stop1; i++, j++) {
-                int cd = (i >= 0 && i < len) ? code(pr.seq[i]) : 4;
-                if (j < Lg) { if (cd < 4) cnt[j][cd] += 1; else for (int h = 0; h < 4; h++) cnt[j][h] += 1; }
+    // The votes of a partial read depend on the evaluated length only through a clip (left reads: rows counted from the
+    // left edge, right reads: from the right edge), so they are piled up once per gap and every length reads the two
+    // tables: cnt[i] = 1 + L[i] + R[Lg-1-i].
+    if (!hostPileBuilt_) {
+        hostPileBuilt_ = true;
+        const int np = (int)std::min<size_t>(in_.partial.size(), 3001);
+        for (int p = 0; p < np; p++) {
+            const PartialRead& pr = in_.partial[p];
+            const int len = (int)pr.seq.size();
+            int ci = pr.clippedIndex;
+            if (repeatflag_[p][0] == 1) ci = repeatflag_[p][2] + repeatflag_[p][1] - 1;
+            if (repeatflag_[p][0] == 2) ci = repeatflag_[p][1];
+            if (pr.match == 1 || pr.match == 4) {
+                const int ext = len - ci - 1;
+                hostAnyLeft_ = true; hostMaxExt_ = std::max(hostMaxExt_, ext);
+                if (ext > (int)hostPileL_.size()) hostPileL_.resize(ext, std::array<int, 4>{{0, 0, 0, 0}});
+                for (int j = 0; j < ext; j++) {
+                    const int i = ci + 1 + j;
+                    const int cd = (i >= 0 && i < len) ? code(pr.seq[i]) : 4;
+                    if (cd < 4) hostPileL_[j][cd] += 1; else for (int h = 0; h < 4; h++) hostPileL_[j][h] += 1;
+                }
+            } else if (pr.match == 2 || pr.match == 3) {
+                hostAnyRight_ = true; hostMaxCi_ = std::max(hostMaxCi_, ci);
+                if (ci > (int)hostPileR_.size()) hostPileR_.resize(ci, std::array<int, 4>{{0, 0, 0, 0}});
+                for (int u = 0; u < ci; u++) {
+                    const int i = ci - 1 - u;
+                    const int cd = (i >= 0 && i < len) ? code(pr.seq[i]) : 4;
+                    if (cd < 4) hostPileR_[u][cd] += 1; else for (int h = 0; h < 4; h++) hostPileR_[u][h] += 1;
+                }
             }
-            if (j - 1 > leftMax) leftMax = j - 1;
-        } else if (pr.match == 2 || pr.match == 3) {
-            int j = Lg - 1;
-            for (int i = ci - 1; i >= stop2; i--, j--) {
-                int cd = (i >= 0 && i < len) ? code(pr.seq[i]) : 4;
-                if (j >= 0 && j < Lg) { if (cd < 4) cnt[j][cd] += 1; else for (int h = 0; h < 4; h++) cnt[j][h] += 1; }
-            }
-            if (j + 1 < rightMin) rightMin = j + 1;
         }
+    }
+    const int leftMax = hostAnyLeft_ ? std::max(std::min(hostMaxExt_, Lg), 0) - 1 : -kMaxGap;
+    const int rightMin = hostAnyRight_ ? Lg - std::min(std::max(hostMaxCi_, 0), Lg) : kMaxGap;
+    std::vector<std::array<int, 4>> cnt(Lg, std::array<int, 4>{{1, 1, 1, 1}});
+    for (int i = 0; i < Lg; i++) {
+        if (i < (int)hostPileL_.size()) for (int k = 0; k < 4; k++) cnt[i][k] += hostPileL_[i][k];
+        const int u = Lg - 1 - i;
+        if (u < (int)hostPileR_.size()) for (int k = 0; k < 4; k++) cnt[i][k] += hostPileR_[u][k];
     }
     int lc = 0, rc = 0;
     char* pl = pileStr_; char* pr = pileStr_ + 100;
@@ -754,6 +775,9 @@ int GapFill::checkGapReads() {
         regionPerct_ = 0;
         evalCandidate(res[i], probes[i], 1);
         lastSoft_ = res[i].soft;
+        // previous_str is a member that run() never resets (Figbird.cpp:3919-3927, 6254): the last probe's final hard consensus
+        // is what the first placeReads call of the next evaluated length is compared with
+        prevStrLen_ = probes[i]; prevStr_ = res[i].hard;
         regionPerctMax_ = regionPerct_;
         if (og_ < 30) { if (validCount_ > thresh) return -1; }
         else { if (validCount_ >= thresh) return -1; }
@@ -889,7 +913,7 @@ void GapFill::finalize(int gl) {
     if ((int)counts_.size() < std::max(endLim, gl)) counts_.resize(std::max(endLim, gl), std::array<double, 5>{{0, 0, 0, 0, 0}});
     for (int i = 0; i < endLim; i++) counts_[i] = std::array<double, 5>{{0, 0, 0, 0, 0}};
     gapLength_ = gl;
-    const int W = a_.maxDistance;
+    const int W = (int)std::min<long>(a_.maxDistance, gapStart);      // left_maxDistance (Figbird.cpp:2272-2277): an unplaced read keeps maxPos = 0
 
     if (a_.unmapped) {
         drawHeader(gapLength_);
@@ -1065,7 +1089,7 @@ GapResult GapFill::run(DeviceQueue& dev, int batchGapIndex) {
         return out;
     };
     if (!prep_.supported) {
-        fprintf(stderr, "figbird_b200: gap %d lies within a read length of a scaffold end; left unfilled\n", in_.rec.gapNo);
+        fprintf(stderr, "figbird_b200: gap %d lies within a read length of a scaffold end (the reference reads outside its window there); left unfilled\n", in_.rec.gapNo);
         return emitUnfilled();
     }
     if (!attempt) return emitUnfilled();    // num_itr=0: one initialize + computeSequence(0,0) => og x 'N' (Figbird.cpp:6223-6233)
@@ -1122,6 +1146,9 @@ GapResult GapFill::run(DeviceQueue& dev, int batchGapIndex) {
                 for (int c = 0; c < chunk && j + c < range; c++) {
                     ItemSpec s = emSpec(gapEstimate + c);
                     if (unmapped && !finalizeFlag) s.flags |= FB_FLAG_EXTRA_PASS;
+                    // the first candidate inherits previous_str from the last checkGapReads probe; it can only match at equal length
+                    // (gapMin == og/2, the first probe, for N-runs of 134..400 bases)
+                    if (unmapped && j == 0 && c == 0 && prevStrLen_ == gapEstimate && gapEstimate > 0) s.stringIn = prevStr_;
                     specs.push_back(s);
                 }
                 dev_->submit(bidx_, specs, chunkRes);

@@ -102,6 +102,7 @@ private:
     std::string draw_;
     std::vector<uint8_t> lastSoft_;         // computeSequence(0,0) of the most recent placeReads call
     int64_t refPlacements_ = 0;
+    int prevStrLen_ = -1; std::vector<uint8_t> prevStr_;    // previous_str as the last checkGapReads probe left it
 
     // constants of setParameters (Figbird.cpp:6157-6165)
     static constexpr int kCov1 = 0, kCov2 = 1, kMatchDiscont = 4, kPartialThreshold = 2, kClipThresh = 2;
@@ -114,6 +115,10 @@ private:
     void pileUp(int Lg, bool makeStrings);
     void initializeEffects(int Lg);     // what initialize() leaves behind on the host besides the gap rows (see ovl_)
     int maxRightCi_ = -1;               // longest right-side pile-up of the gap (-1: not computed yet)
+    // update_partial_prob's vote tables of the gap (host copy, built on first use): rows from the left / right edge
+    bool hostPileBuilt_ = false, hostAnyLeft_ = false, hostAnyRight_ = false;
+    int hostMaxExt_ = -(1 << 30), hostMaxCi_ = -(1 << 30);
+    std::vector<std::array<int, 4>> hostPileL_, hostPileR_;
     void setConcensus(const std::vector<uint8_t>& codes, int len);
     void copyStr(std::vector<char>& dst, const std::vector<char>& src);
     ItemSpec emSpec(int Lg) const;

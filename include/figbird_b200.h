@@ -129,7 +129,8 @@ typedef struct {
     int32_t flags;              /* FB_FLAG_* */
     int32_t comp_count_in;      /* RESUME: comp_count carried in */
     const double* counts_in;    /* RESUME: countsGap gap rows [Lg][5] to start the M-step from */
-    const uint8_t* string_in;   /* HARD: the gap string (codes, [Lg]); RESUME: previous hard consensus ([Lg]) */
+    const uint8_t* string_in;   /* HARD: the gap string (codes, [Lg]); EM: previous hard consensus ([Lg]) the first call is compared
+                                   with (previous_str, Figbird.cpp:3919-3927), or NULL for none */
 } FbWorkItem;
 
 /* Result header; arrays follow in the same engine-owned pinned arena at the given byte offsets from the

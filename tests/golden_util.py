@@ -6,7 +6,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLDEN = os.path.join(HERE, "golden")
-NAMES = ("g1", "g2", "g3", "g4", "g5", "g6", "g7")
+NAMES = ("g1", "g2", "g3", "g4", "g5", "g6", "g7", "g8", "g9")
 
 
 def extract(name, dest):

@@ -32,6 +32,12 @@ CASES = {
     # 150-base reads with right-side pile-ups of more than 105 bases: update_partial_prob overruns partial_right into the
     # saved-read indices that finalize() reads (Figbird.cpp:1625-1627, 2063-2084, 5345); the host reproduces that layout
     "g7": dict(gen={"genome": 45000, "gaplist": "150,230,118", "seed": 58, "cov": 40, "sd": 50, "readN": 10}, readlen=150, insert=500),
+    # scaffold ends: the reference clips its window there (initialize_start_end, Figbird.cpp:2268-2296).  Three scaffolds whose
+    # first gap starts 120 / 300 / 3000 bases from the left end and whose last gap (N-run > 400: one candidate length in both
+    # modes) ends read length + 10 bases before the right end; g8 under the 200 bp library (maxDistance 200 / 230: the first is
+    # clipped on the left, every last gap on the right), g9 under the 3500 bp library (3500 / 4025: all of them clipped)
+    "g8": dict(gen={"genome": 36000, "scaffolds": 3, "gaplist": "45,520,150,560,25,610", "gappos": "120,-110,300,-110,3000,-110", "seed": 61, "cov": 30}, readlen=100, insert=200),
+    "g9": dict(gen={"genome": 60000, "scaffolds": 3, "minsep": 200, "gaplist": "60,540,130,600,35,520", "gappos": "120,-110,300,-110,3000,-110", "seed": 62, "cov": 20, "sd": 350}, readlen=100, insert=3500),
     "g6": dict(gen={"genome": 90000, "gaplist": "5000,3000,1500", "seed": 52, "cov": 20, "sd": 350}, readlen=100, insert=3500),
 }
 

@@ -46,6 +46,46 @@ def test_oracle_matches_reference_outputs(case, mode):
     assert worst <= 1e-9, "countsGap relative error %g" % worst
 
 
+def _chains(dump):
+    """{(gapstart, Lg): [placeReads calls of the 1st, 2nd, ... EM chain run at that length]} from an FB_ORACLE_DUMP file."""
+    out = {}
+    with open(dump) as f:
+        for line in f:
+            if line.startswith("CALL"):
+                t = line.split()
+                key, rnd = (int(t[2]), int(t[4])), int(t[6])
+                if rnd == 0:
+                    out.setdefault(key, []).append(1)
+                else:
+                    out[key][-1] += 1
+    return out
+
+
+@pytest.mark.parametrize("mode", ["partial", "unmapped"])
+def test_em_chain_lengths_match_reference(case, mode):
+    """Every EM chain the reference ran (one initialize() + its placeReads calls, from the dump-instrumented worker:
+    tests/golden/callcounts.json, tests/make_callcounts.py) is run by the host replay with the same number of calls --
+    the comp_count stop rule including previous_str carried over from the checkGapReads probes (Figbird.cpp:3919-3927,
+    6121-6153).  Speculative probes and candidates past the reference's early exit may add chains, never change one: the reference's
+    chains of a (gap, length) must appear among ours in order."""
+    import json
+    ref = json.load(open(os.path.join(gu.GOLDEN, "callcounts.json")))[os.path.basename(case)][mode]
+    dump = os.path.join(case, "oracle_chains_%s.txt" % mode)
+    if os.path.exists(dump):
+        os.remove(dump)
+    fc.run_ours(case, mode, fc.oracle_exe(), extra_env={"FB_ORACLE_DUMP": dump}, name="chains")
+    mine = _chains(dump)
+    want = {}
+    for gs, Lg, n in ref:
+        want.setdefault((gs, Lg), []).append(n)
+    assert want, "empty reference call list"
+    def subseq(v, m):      # ours may hold extra chains (speculative probes / candidates past an early exit), in order
+        it = iter(m)
+        return all(any(x == y for y in it) for x in v)
+    bad = [(k, v, mine.get(k, [])) for k, v in want.items() if not subseq(v, mine.get(k, []))]
+    assert not bad, "EM chains differ from the reference's (key, reference, ours): %r" % bad[:5]
+
+
 LIGHT = ("g1", "g2", "g4")      # the host-logic tests below repeat whole runs: small fixtures keep the CPU suite to a few minutes
 
 

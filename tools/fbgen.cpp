@@ -47,6 +47,7 @@ struct Opt {
     double mu = 200, sd = 20, cov = 30; uint64_t seed = 1; int x1 = -1, x2 = -1; double e0 = 0.005, e1 = 0.02;
     double negfrac = 0; int negmax = 30; long model_pairs = -1; int near = -1; std::string out = "."; int minsep = -1;
     std::string gaplist;  // optional explicit comma list of true gap lengths
+    std::string gappos;   // with --gaplist: explicit truth start positions (>= 0: from the scaffold start; < 0: -d puts the gap end d bases before the scaffold end)
     int lib = 0;          // library tag in read names
     int nreadN = 0;       // 1 in nreadN reads gets an 'N' base (0 = never)
 };
@@ -63,7 +64,7 @@ int main(int argc, char** argv) {
         else if (k == "--seed") o.seed = strtoull(v, 0, 10); else if (k == "--x1") o.x1 = atoi(v); else if (k == "--x2") o.x2 = atoi(v);
         else if (k == "--negfrac") o.negfrac = atof(v); else if (k == "--negmax") o.negmax = atoi(v); else if (k == "--model-pairs") o.model_pairs = atol(v);
         else if (k == "--near") o.near = atoi(v); else if (k == "--out") o.out = v; else if (k == "--minsep") o.minsep = atoi(v);
-        else if (k == "--gaplist") o.gaplist = v; else if (k == "--lib") o.lib = atoi(v); else if (k == "--readN") o.nreadN = atoi(v);
+        else if (k == "--gaplist") o.gaplist = v; else if (k == "--gappos") o.gappos = v; else if (k == "--lib") o.lib = atoi(v); else if (k == "--readN") o.nreadN = atoi(v);
         else if (k == "--e0") o.e0 = atof(v); else if (k == "--e1") o.e1 = atof(v);
         else { fprintf(stderr, "fbgen: unknown option %s\n", k.c_str()); return 2; }
     }
@@ -78,6 +79,9 @@ int main(int argc, char** argv) {
 
     std::vector<int> explicit_gaps;
     if (!o.gaplist.empty()) { const char* p = o.gaplist.c_str(); while (*p) { explicit_gaps.push_back(atoi(p)); while (*p && *p != ',') p++; if (*p) p++; } o.ngaps = (int)explicit_gaps.size(); }
+
+    std::vector<long> explicit_pos;
+    if (!o.gappos.empty()) { const char* p = o.gappos.c_str(); while (*p) { explicit_pos.push_back(atol(p)); while (*p && *p != ',') p++; if (*p) p++; } }
 
     // ---- scaffolds + gaps
     std::vector<Scaf> sc(o.nscaf);
@@ -101,6 +105,7 @@ int main(int argc, char** argv) {
                 long lo = g * slot + o.minsep, hi = (g + 1) * slot - o.minsep - (neg ? 0 : tl);
                 if (hi <= lo) { fprintf(stderr, "fbgen: slot too small for gap (slot %ld, minsep %d, len %d)\n", slot, o.minsep, tl); return 2; }
                 G.tstart = lo + (long)rng.below(hi - lo);
+                if (gi < (int)explicit_pos.size()) { const long v = explicit_pos[gi]; G.tstart = v >= 0 ? v : per + v - (neg ? 0 : tl); }      // scaffold-end cases: the caller keeps them sorted and apart
                 if (neg) { G.ov = 5 + (int)rng.below(21); G.tlen = 0; G.og = 1 + (int)rng.below(o.negmax); }
                 else { G.ov = 0; G.tlen = tl; G.og = std::max(1, (int)std::lround(tl * (0.8 + 0.4 * rng.uni()))); }
                 S.gaps.push_back(G);
