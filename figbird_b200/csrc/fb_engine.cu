@@ -1121,6 +1121,7 @@ struct fb_ctx {
     std::string err;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t evDone = nullptr;                 // blocking-sync event: the host thread sleeps while a launch runs (several lanes and GPUs share the host cores)
     cudaStream_t bstream[kNumBuckets + 1] = {};   // one stream per shared-memory bucket (+1: global-table items)
     cudaEvent_t bev[kNumBuckets + 1] = {};
     int smemOptin = 0;
@@ -1162,6 +1163,7 @@ extern "C" fb_status fb_ctx_create(int32_t device, fb_ctx** out) {
     c->smemOptin = (int)pr.sharedMemPerBlockOptin;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
+    CK(cudaEventCreateWithFlags(&c->evDone, cudaEventBlockingSync | cudaEventDisableTiming));
     CK(cudaFuncSetAttribute(fb_em_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     CK(cudaFuncSetAttribute(fb_em_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     for (int b = 0; b <= kNumBuckets; b++) { CK(cudaStreamCreateWithFlags(&c->bstream[b], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->bev[b], cudaEventDisableTiming)); }
@@ -1186,6 +1188,7 @@ extern "C" void fb_ctx_destroy(fb_ctx* c) {
     for (int b = 0; b <= kNumBuckets; b++) { if (c->bstream[b]) cudaStreamDestroy(c->bstream[b]); if (c->bev[b]) cudaEventDestroy(c->bev[b]); }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->evDone) cudaEventDestroy(c->evDone);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1454,7 +1457,8 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
     CK(cudaMemcpyAsync(c->h_out, c->d_out.p, outTotal, cudaMemcpyDeviceToHost, c->stream));
     unsigned long long hc[32] = {0};
     CK(cudaMemcpyAsync(hc, c->d_ctr.p, sizeof hc, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventRecord(c->evDone, c->stream));
+    CK(cudaEventSynchronize(c->evDone));
     float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->ctr.device_ms += ms; c->ctr.kernel_launches += launches; c->ctr.d2h_bytes += (int64_t)outTotal;
     if (c->device < 64) {

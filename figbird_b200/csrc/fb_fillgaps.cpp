@@ -422,15 +422,27 @@ int fillgapsMain(int argc, const char* const* argv) {
         }
         rs.dev.h2d_bytes += devCtr[d].h2d_bytes; rs.dev.d2h_bytes += devCtr[d].d2h_bytes; rs.dev.lane_steps_p1 += devCtr[d].lane_steps_p1; rs.dev.lane_steps_p2 += devCtr[d].lane_steps_p2; rs.ticks += devTicks[d]; rs.tEngine = std::max(rs.tEngine, devEng[d]); rs.tCopy = std::max(rs.tCopy, devCopy[d]); rs.tCtx = std::max(rs.tCtx, devCtx[d]); rs.tWorkers = std::max(rs.tWorkers, devWork[d]); rs.cpuWorkers += devCpu[d];
     }
+    std::string perGpu;      // kernel time (union of the kernel intervals) of every GPU of the run, in FIGBIRD_GPUS order
+    {
+        std::vector<int> seen;
+        for (int d = 0; d < nD; d++) {
+            if (std::find(seen.begin(), seen.end(), devs[d]) != seen.end()) continue;
+            seen.push_back(devs[d]);
+            double u = 0, sum = 0;
+            for (int e2 = 0; e2 < nD; e2++) if (devs[e2] == devs[d]) { u = std::max(u, devCtr[e2].device_union_ms); sum += devCtr[e2].device_ms; }
+            char b[64]; snprintf(b, sizeof b, "%s%.6f", perGpu.empty() ? "" : ", ", u > 0 ? u : sum);
+            perGpu += b;
+        }
+    }
     if (const char* mp = getenv("FIGBIRD_METRICS")) {
         FILE* mf = fopen(mp, "w");
         if (mf) {
             fprintf(mf, "{\"engine\": \"%s\", \"gaps\": %d, \"gpus\": %d, \"t_load\": %.6f, \"t_model\": %.6f, \"t_prepare\": %.6f, \"t_fill\": %.6f, \"t_write\": %.6f, \"t_engine_calls\": %.6f, \"t_result_copy\": %.6f, \"t_ctx_upload\": %.6f, \"t_workers\": %.6f, \"cpu_workers\": %.6f, "
                         "\"ref_placements_p1\": %lld, \"dev_placements_p1\": %lld, \"dev_placements_p2\": %lld, \"dev_base_terms\": %lld, \"kernel_launches\": %lld, "
-                        "\"device_ms\": %.6f, \"h2d_bytes\": %lld, \"d2h_bytes\": %lld, \"ticks\": %lld, \"lane_steps_p1\": %lld, \"lane_steps_p2\": %lld}\n",
+                        "\"device_ms\": %.6f, \"h2d_bytes\": %lld, \"d2h_bytes\": %lld, \"ticks\": %lld, \"lane_steps_p1\": %lld, \"lane_steps_p2\": %lld, \"device_ms_per_gpu\": [%s]}\n",
                     fb_engine_name(), nG, nD, rs.tLoad, rs.tModel, rs.tPrep, rs.tFill, rs.tWrite, rs.tEngine, rs.tCopy, rs.tCtx, rs.tWorkers, rs.cpuWorkers, (long long)rs.refPlacements, (long long)rs.dev.placements_p1,
                     (long long)rs.dev.placements_p2, (long long)rs.dev.base_terms, (long long)rs.dev.kernel_launches, rs.dev.device_ms, (long long)rs.dev.h2d_bytes,
-                    (long long)rs.dev.d2h_bytes, (long long)rs.ticks, (long long)rs.dev.lane_steps_p1, (long long)rs.dev.lane_steps_p2);
+                    (long long)rs.dev.d2h_bytes, (long long)rs.ticks, (long long)rs.dev.lane_steps_p1, (long long)rs.dev.lane_steps_p2, perGpu.c_str());
             fclose(mf);
         }
     }

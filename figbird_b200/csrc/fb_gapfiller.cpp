@@ -1122,6 +1122,7 @@ GapResult GapFill::run(DeviceQueue& dev, int batchGapIndex) {
     if (fillOrNot != 0) {
         gapLength_ = 0;
         out.gapStringLength = 0; out.gapString.clear(); out.gapToFill = fillOrNot; out.drawText = draw_;
+        out.refPlacements = refPlacements_;      // the checkGapReads probes ran before initialize() found the overlap
         return out;
     }
 

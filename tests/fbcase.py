@@ -35,7 +35,7 @@ def build_tools():
     exe = os.path.join(TBUILD, "fbgen")
     src = os.path.join(ROOT, "tools", "fbgen.cpp")
     if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src):
-        sh(["g++", "-O2", "-std=c++17", "-w", "-o", exe, src])
+        sh(["g++", "-O2", "-std=c++17", "-w", "-pthread", "-o", exe, src])
     return exe
 
 
@@ -71,13 +71,24 @@ def make_case(case, gen_args, readlen=100, insert=200, maxdist_local=None):
         shutil.rmtree(d, ignore_errors=True)
         os.makedirs(os.path.join(d, "Temp"))
     p = os.path.join(case, "partial")
-    os.makedirs(os.path.join(p, "Gaps"))
-    sh([os.path.join(REF, "Preprocess"), draft, str(x1), "1", os.path.join(case, "result1.sam"), os.path.join(p, "myout.sam"), draft,
-        "r1.fq", "r2.fq", os.path.join(p, "Gaps") + "/", os.path.join(p, "Temp") + "/", "1", "0", "0"], cwd=case)
     u = os.path.join(case, "unmapped")
-    shutil.copytree(os.path.join(p, "Gaps"), os.path.join(u, "Gaps"))
-    sh([os.path.join(REF, "Preprocess"), draft, str(x2), "2", os.path.join(case, "result2.sam"), os.path.join(u, "myout.sam"), draft,
-        "r1.fq", "r2.fq", os.path.join(u, "Gaps") + "/", os.path.join(u, "Temp") + "/", "1", "0", "0"], cwd=case)
+    os.makedirs(os.path.join(p, "Gaps")); os.makedirs(os.path.join(u, "Gaps"))
+    # the two Preprocess passes (RunFigbird.sh:285 mode 1, :338 mode 2) are independent: run them side by side
+    cmds = [[os.path.join(REF, "Preprocess"), draft, str(x1), "1", os.path.join(case, "result1.sam"), os.path.join(p, "myout.sam"), draft,
+             "r1.fq", "r2.fq", os.path.join(p, "Gaps") + "/", os.path.join(p, "Temp") + "/", "1", "0", "0"],
+            [os.path.join(REF, "Preprocess"), draft, str(x2), "2", os.path.join(case, "result2.sam"), os.path.join(u, "myout.sam"), draft,
+             "r1.fq", "r2.fq", os.path.join(u, "Gaps") + "/", os.path.join(u, "Temp") + "/", "1", "0", "0"]]
+    procs = [subprocess.Popen(c, cwd=case, stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for c in cmds]
+    for c, pr in zip(cmds, procs):
+        out = pr.communicate()[0]
+        if pr.returncode != 0:
+            raise RuntimeError("command failed (%d): %s\n%s" % (pr.returncode, " ".join(c), out.decode(errors="replace")[-4000:]))
+    # FillGaps needs partial_gaps_<g>.sam for every gap in unmapped mode too (Figbird.cpp:1801,1915): the script keeps one Gaps/
+    # directory across both passes; here the unmapped run's directory gets links to the partial pass's files
+    for f in os.listdir(os.path.join(p, "Gaps")):
+        dst = os.path.join(u, "Gaps", f)
+        if not os.path.exists(dst):
+            os.link(os.path.join(p, "Gaps", f), dst)
     with open(os.path.join(case, "params.txt"), "w") as f:
         f.write("readlen %d\ninsert %d\nx1 %d\nx2 %d\n" % (readlen, insert, x1, x2))
     return case

@@ -23,7 +23,11 @@ def test_product_matches_reference_golden(case, mode):
     exp = gu.expected(case, mode)
     for f in ("gapout.txt", "filledContigs.fa", "Ncount.txt", "draw.txt"):
         assert o[f] == exp[f], "%s differs from the reference (%s mode)" % (f, mode)
-    assert '"engine": "cuda-sm100a"' in open(os.path.join(case, "m_%s.json" % mode)).read()
+    import json
+    m = json.load(open(os.path.join(case, "m_%s.json" % mode)))
+    assert m["engine"] == "cuda-sm100a"
+    # the reference's own count of pass-1 placements (counter-instrumented worker, tests/golden/placements.json)
+    assert m["ref_placements_p1"] == json.load(open(os.path.join(gu.GOLDEN, "placements.json")))[os.path.basename(case)][mode]
 
 
 def test_in_process_entry_point(case):
@@ -100,7 +104,7 @@ def test_c2_full_size_against_reference_golden(tmp_path_factory):
     import hashlib
     import bench
     d = tmp_path_factory.mktemp("c2")
-    case = bench.prepare_case(str(d / "c2"), bench.WORKLOADS["c2"], 102)
+    case = bench.prepare_case(str(d / "c2"), bench.WORKLOADS["c2n"], 102)
     md5s = open(os.path.join(gu.GOLDEN, "c2_filled.md5")).read().split()
     for i, mode in enumerate(("partial", "unmapped")):
         o = fc.run_ours(case, mode, fc.product_exe(), threads=8)

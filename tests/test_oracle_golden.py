@@ -24,10 +24,16 @@ def case(request, tmp_path_factory):
 def test_oracle_matches_reference_outputs(case, mode):
     dump = os.path.join(case, "oracle_counts_%s.txt" % mode)
     model = os.path.join(case, "oracle_model_%s.txt" % mode)
-    o = fc.run_ours(case, mode, fc.oracle_exe(), extra_env={"FB_ORACLE_DUMP": dump, "FIGBIRD_DUMP_MODEL": model}, name="oracle")
+    metrics = os.path.join(case, "oracle_metrics_%s.json" % mode)
+    o = fc.run_ours(case, mode, fc.oracle_exe(), extra_env={"FB_ORACLE_DUMP": dump, "FIGBIRD_DUMP_MODEL": model, "FIGBIRD_METRICS": metrics}, name="oracle")
     exp = gu.expected(case, mode)
     for f in ("gapout.txt", "filledContigs.fa", "Ncount.txt", "draw.txt"):
         assert o[f] == exp[f], "%s differs from the reference (%s mode)" % (f, mode)
+    # pass-1 placements the reference scan consumed: the host replay's count against the reference's own counters
+    # (oracle/count_patch.awk at Figbird.cpp:3169,3236,3591,3658; tests/golden/placements.json)
+    import json
+    want = json.load(open(os.path.join(gu.GOLDEN, "placements.json")))[os.path.basename(case)][mode]
+    assert json.load(open(metrics))["ref_placements_p1"] == want
     # model tables
     assert gu.model_lines(model) == gu.model_lines(os.path.join(case, "expected", mode, "model.txt"))
     # per-position base weights

@@ -25,6 +25,11 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdarg>
+#include <mutex>
+#include <thread>
 
 struct Rng {
     uint64_t s[4];
@@ -50,6 +55,8 @@ struct Opt {
     std::string gappos;   // with --gaplist: explicit truth start positions (>= 0: from the scaffold start; < 0: -d puts the gap end d bases before the scaffold end)
     int lib = 0;          // library tag in read names
     int nreadN = 0;       // 1 in nreadN reads gets an 'N' base (0 = never)
+    int threads = -1;     // -1: one RNG stream, one thread (the byte-stable legacy layout the fixtures were made with); >= 0: one RNG stream per
+                          // scaffold, scaffolds generated on `threads` threads (0 = all cores); output still deterministic for a seed
 };
 
 struct Aln { bool ok = false; long pos = 0; std::string cigar, md; int nm = 0, as = 0; long rstart = 0, rend = 0; };  // pos 1-based draft; rstart/rend: draft extent incl. soft clips
@@ -65,7 +72,7 @@ int main(int argc, char** argv) {
         else if (k == "--negfrac") o.negfrac = atof(v); else if (k == "--negmax") o.negmax = atoi(v); else if (k == "--model-pairs") o.model_pairs = atol(v);
         else if (k == "--near") o.near = atoi(v); else if (k == "--out") o.out = v; else if (k == "--minsep") o.minsep = atoi(v);
         else if (k == "--gaplist") o.gaplist = v; else if (k == "--gappos") o.gappos = v; else if (k == "--lib") o.lib = atoi(v); else if (k == "--readN") o.nreadN = atoi(v);
-        else if (k == "--e0") o.e0 = atof(v); else if (k == "--e1") o.e1 = atof(v);
+        else if (k == "--threads") o.threads = atoi(v); else if (k == "--e0") o.e0 = atof(v); else if (k == "--e1") o.e1 = atof(v);
         else { fprintf(stderr, "fbgen: unknown option %s\n", k.c_str()); return 2; }
     }
     if (o.sd <= 0) o.sd = 0.1 * o.mu;
@@ -73,7 +80,7 @@ int main(int argc, char** argv) {
     if (o.x2 < 0) o.x2 = (int)(1.15 * o.mu);        // RunFigbird.sh:193-217,333  -X 1.15*insert
     int maxins = (int)(o.mu + 6 * o.sd);
     if (o.minsep < 0) o.minsep = (int)(1.15 * maxins) + o.L + 50;
-    Rng rng(o.seed);
+    Rng rng0(o.seed);
     const int L = o.L;
     const char B[4] = {'A', 'C', 'G', 'T'};
 
@@ -87,10 +94,14 @@ int main(int argc, char** argv) {
     std::vector<Scaf> sc(o.nscaf);
     long per = o.genome / o.nscaf;
     int gi = 0;
+    const bool par = o.threads >= 0;
+    auto scafSeed = [&](int s, int what) { return o.seed * 0x9e3779b97f4a7c15ULL + (uint64_t)s * 2 + what + 1; };
     for (int s = 0; s < o.nscaf; s++) {
         Scaf& S = sc[s];
         S.name = "scaffold_" + std::to_string(s + 1);
         S.truth.resize(per);
+        Rng srng(scafSeed(s, 0));
+        Rng& rng = par ? srng : rng0;
         for (long i = 0; i < per; i++) S.truth[i] = B[rng.next() >> 62];
         int ng = o.ngaps / o.nscaf + (s < o.ngaps % o.nscaf ? 1 : 0);
         if (ng > 0) {
@@ -141,10 +152,17 @@ int main(int argc, char** argv) {
     static char b1[1 << 22], b2[1 << 22]; setvbuf(s1, b1, _IOFBF, sizeof b1); setvbuf(s2, b2, _IOFBF, sizeof b2);
     for (FILE* f : {s1, s2}) { fprintf(f, "@HD\tVN:1.0\tSO:unsorted\n"); for (auto& S : sc) fprintf(f, "@SQ\tSN:%s\tLN:%zu\n", S.name.c_str(), S.draft.size()); fprintf(f, "@PG\tID:bowtie2\tPN:bowtie2\tVN:2.2.3\n"); }
 
-    long pair_id = 0, far_written = 0;
-    for (int s = 0; s < o.nscaf; s++) {
+    struct Buf { std::string a, b; };
+    auto appendf = [](std::string& dst, const char* fmt, ...) {
+        char tmp[4096]; va_list ap; va_start(ap, fmt); int n = vsnprintf(tmp, sizeof tmp, fmt, ap); va_end(ap);
+        if (n >= (int)sizeof tmp) { std::string big((size_t)n + 1, '\0'); va_start(ap, fmt); vsnprintf(&big[0], big.size(), fmt, ap); va_end(ap); dst.append(big.c_str(), (size_t)n); }
+        else if (n > 0) dst.append(tmp, (size_t)n);
+    };
+    auto pairsOf = [&](int s) { return (long)(o.cov * (double)sc[s].truth.size() / (2.0 * L)); };
+    // reads of one scaffold -> SAM text of both files.  rng / far_written: the shared stream and counter (legacy) or the scaffold's own
+    auto genReads = [&](int s, Rng& rng, long pair_id, long& far_written, long far_cap, Buf& buf) {
         Scaf& S = sc[s];
-        long npairs = (long)(o.cov * (double)S.truth.size() / (2.0 * L));
+        long npairs = pairsOf(s);
         // truth -> draft coordinate of a truth position left of / right of each gap
         auto align = [&](long ts, const std::string& rd_ref /*read in reference orientation*/, bool local) -> Aln {
             // ts: truth start of the read (reference orientation), covers [ts, ts+L)
@@ -206,11 +224,11 @@ int main(int argc, char** argv) {
             if (o.near >= 0) {
                 bool nearg = false;
                 for (auto& G : S.gaps) { long a = G.tstart - o.near, b = G.tstart + G.tlen + o.near; if (f < b && f + isz > a) { nearg = true; break; } if (G.tstart - o.near > f + isz) break; }
-                if (!nearg) { if (o.model_pairs >= 0 && far_written >= o.model_pairs) continue; far_written++; }
+                if (!nearg) { if (far_cap >= 0 && far_written >= far_cap) continue; far_written++; }
             }
             char qn[64]; snprintf(qn, sizeof qn, "r%d_%ld", o.lib, pair_id);
             for (int mode = 0; mode < 2; mode++) {
-                FILE* out = mode == 0 ? s1 : s2; bool local = mode == 0; int X = local ? o.x1 : o.x2;
+                std::string& out = mode == 0 ? buf.a : buf.b; bool local = mode == 0; int X = local ? o.x1 : o.x2;
                 Aln al = align(f, lr, local), ar = align(f + isz - L, rr, local);
                 // mate1 = left/forward if m1fwd else right/reverse
                 const Aln& a1 = m1fwd ? al : ar; const Aln& a2 = m1fwd ? ar : al;
@@ -230,19 +248,58 @@ int main(int argc, char** argv) {
                     const std::string& sref = m == 0 ? seq1ref : seq2ref; const std::string& qref = m == 0 ? q1ref : q2ref;
                     if (me.ok) {
                         long t = 0; if (mate.ok) { t = (me.rstart <= mate.rstart && !(me.rstart == mate.rstart && m == 1)) ? tl : -tl; }
-                        fprintf(out, "%s\t%d\t%s\t%ld\t%d\t%s\t%s\t%ld\t%ld\t%s\t%s\tAS:i:%d\tXN:i:0\tXM:i:%d\tXO:i:0\tXG:i:0\tNM:i:%d\tMD:Z:%s\tYT:Z:%s\n",
+                        appendf(out, "%s\t%d\t%s\t%ld\t%d\t%s\t%s\t%ld\t%ld\t%s\t%s\tAS:i:%d\tXN:i:0\tXM:i:%d\tXO:i:0\tXG:i:0\tNM:i:%d\tMD:Z:%s\tYT:Z:%s\n",
                                 qn, flag, S.name.c_str(), me.pos, 42, me.cigar.c_str(), mate.ok ? "=" : "=", mate.ok ? mate.pos : me.pos, t,
                                 sref.c_str(), qref.c_str(), me.as, me.nm, me.nm, me.md.c_str(), conc ? "CP" : (mate.ok ? "DP" : "UP"));
                     } else {
                         std::string sq = asseq(sref, rev), qq = asq(qref, rev);
-                        if (mate.ok) fprintf(out, "%s\t%d\t%s\t%ld\t0\t*\t=\t%ld\t0\t%s\t%s\tYT:Z:UP\n", qn, flag, S.name.c_str(), mate.pos, mate.pos, sq.c_str(), qq.c_str());
-                        else fprintf(out, "%s\t%d\t*\t0\t0\t*\t*\t0\t0\t%s\t%s\tYT:Z:UP\n", qn, flag, sq.c_str(), qq.c_str());
+                        if (mate.ok) appendf(out, "%s\t%d\t%s\t%ld\t0\t*\t=\t%ld\t0\t%s\t%s\tYT:Z:UP\n", qn, flag, S.name.c_str(), mate.pos, mate.pos, sq.c_str(), qq.c_str());
+                        else appendf(out, "%s\t%d\t*\t0\t0\t*\t*\t0\t0\t%s\t%s\tYT:Z:UP\n", qn, flag, sq.c_str(), qq.c_str());
                     }
                 }
             }
         }
+    };
+    long total_pairs = 0;
+    if (!par) {
+        long pair_id = 0, far_written = 0;
+        for (int s = 0; s < o.nscaf; s++) {
+            Buf buf;
+            genReads(s, rng0, pair_id, far_written, o.model_pairs, buf);
+            pair_id += pairsOf(s);
+            fwrite(buf.a.data(), 1, buf.a.size(), s1); fwrite(buf.b.data(), 1, buf.b.size(), s2);
+        }
+        total_pairs = pair_id;
+    } else {
+        // one RNG stream and one share of the model pairs per scaffold; worker threads fill buffers, this thread writes them in order
+        int nt = o.threads > 0 ? o.threads : (int)std::thread::hardware_concurrency();
+        nt = std::max(1, std::min(nt, o.nscaf));
+        std::vector<long> base(o.nscaf + 1, 0);
+        for (int s = 0; s < o.nscaf; s++) base[s + 1] = base[s] + pairsOf(s);
+        total_pairs = base[o.nscaf];
+        std::vector<Buf> bufs(o.nscaf); std::vector<char> ready(o.nscaf, 0);
+        std::mutex mu; std::condition_variable cv; std::atomic<int> next(0); int written = 0;
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) th.emplace_back([&] {
+            for (int s; (s = next++) < o.nscaf;) {
+                { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return s < written + 2 * nt; }); }      // bound the text held in memory
+                Rng r(scafSeed(s, 1)); long far = 0;
+                const long cap = o.model_pairs >= 0 ? o.model_pairs / o.nscaf + (s < o.model_pairs % o.nscaf ? 1 : 0) : -1;
+                genReads(s, r, base[s], far, cap, bufs[s]);
+                { std::lock_guard<std::mutex> l(mu); ready[s] = 1; }
+                cv.notify_all();
+            }
+        });
+        for (int s = 0; s < o.nscaf; s++) {
+            { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return ready[s] != 0; }); }
+            fwrite(bufs[s].a.data(), 1, bufs[s].a.size(), s1); fwrite(bufs[s].b.data(), 1, bufs[s].b.size(), s2);
+            Buf().a.swap(bufs[s].a); Buf().b.swap(bufs[s].b);
+            { std::lock_guard<std::mutex> l(mu); written = s + 1; }
+            cv.notify_all();
+        }
+        for (auto& t : th) t.join();
     }
     fclose(s1); fclose(s2);
-    fprintf(stderr, "fbgen: %ld pairs, %d scaffolds, %d gaps -> %s\n", pair_id, o.nscaf, o.ngaps, o.out.c_str());
+    fprintf(stderr, "fbgen: %ld pairs, %d scaffolds, %d gaps -> %s\n", total_pairs, o.nscaf, o.ngaps, o.out.c_str());
     return 0;
 }
