@@ -1124,6 +1124,9 @@ struct fb_ctx {
     cudaEvent_t evDone = nullptr;                 // blocking-sync event: the host thread sleeps while a launch runs (several lanes and GPUs share the host cores)
     cudaStream_t bstream[kNumBuckets + 1] = {};   // one stream per shared-memory bucket (+1: global-table items)
     cudaEvent_t bev[kNumBuckets + 1] = {};
+    cudaEvent_t bev0[kNumBuckets + 1] = {};      // diagnostics (FIGBIRD_BUCKET_STATS): start of each bucket's launch
+    double bucketMs[kNumBuckets + 1] = {}; long long bucketItems[kNumBuckets + 1] = {}, bucketLaunches[kNumBuckets + 1] = {};
+    bool bucketStats = false;
     int smemOptin = 0;
     bool haveModel = false, haveBatch = false;
     DevModel dm{};
@@ -1166,7 +1169,12 @@ extern "C" fb_status fb_ctx_create(int32_t device, fb_ctx** out) {
     CK(cudaEventCreateWithFlags(&c->evDone, cudaEventBlockingSync | cudaEventDisableTiming));
     CK(cudaFuncSetAttribute(fb_em_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     CK(cudaFuncSetAttribute(fb_em_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    for (int b = 0; b <= kNumBuckets; b++) { CK(cudaStreamCreateWithFlags(&c->bstream[b], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->bev[b], cudaEventDisableTiming)); }
+    c->bucketStats = getenv("FIGBIRD_BUCKET_STATS") != nullptr;
+    for (int b = 0; b <= kNumBuckets; b++) {
+        CK(cudaStreamCreateWithFlags(&c->bstream[b], cudaStreamNonBlocking));
+        if (c->bucketStats) { CK(cudaEventCreate(&c->bev[b])); CK(cudaEventCreate(&c->bev0[b])); }
+        else CK(cudaEventCreateWithFlags(&c->bev[b], cudaEventDisableTiming));
+    }
     CK(c->d_ctr.ensure(32)); CK(cudaMemset(c->d_ctr.p, 0, 32 * sizeof(unsigned long long)));
     if (device < 64) {
         DevClock& k = g_clock[device]; std::lock_guard<std::mutex> l(k.mu);
@@ -1185,7 +1193,7 @@ extern "C" void fb_ctx_destroy(fb_ctx* c) {
     c->d_items.release(); c->d_in.release(); c->d_out.release(); c->d_scratch.release(); c->d_ctr.release();
     if (c->h_out) cudaFreeHost(c->h_out);
     if (c->h_in) cudaFreeHost(c->h_in);
-    for (int b = 0; b <= kNumBuckets; b++) { if (c->bstream[b]) cudaStreamDestroy(c->bstream[b]); if (c->bev[b]) cudaEventDestroy(c->bev[b]); }
+    for (int b = 0; b <= kNumBuckets; b++) { if (c->bstream[b]) cudaStreamDestroy(c->bstream[b]); if (c->bev[b]) cudaEventDestroy(c->bev[b]); if (c->bev0[b]) cudaEventDestroy(c->bev0[b]); }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->evDone) cudaEventDestroy(c->evDone);
@@ -1325,6 +1333,11 @@ extern "C" fb_status fb_batch_upload(fb_ctx* c, const FbGapBatch* b) {
 extern "C" fb_status fb_get_counters(const fb_ctx* c, FbCounters* out) {
     if (!c || !out) return FB_ERR_ARG;
     *out = c->ctr;
+    if (c->bucketStats) {
+        fprintf(stderr, "bucket stats dev %d (cumulative; buckets overlap on the device): total %.0f ms |", c->device, c->ctr.device_ms);
+        for (int b = 0; b <= kNumBuckets; b++) fprintf(stderr, " b%d%s: %.0f ms %lld items %lld launches |", b, b == kNumBuckets ? "(global tables)" : "", c->bucketMs[b], c->bucketItems[b], c->bucketLaunches[b]);
+        fprintf(stderr, "\n");
+    }
     if (c->device < 64) { DevClock& k = g_clock[c->device]; std::lock_guard<std::mutex> l(k.mu); out->device_union_ms = k.unionMs; }
     return FB_OK;
 }
@@ -1446,6 +1459,7 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
     for (int b = 0; b <= kNumBuckets; b++) {
         if (!bucketCount[b]) continue;
         CK(cudaStreamWaitEvent(c->bstream[b], c->ev0, 0));
+        if (c->bucketStats) CK(cudaEventRecord(c->bev0[b], c->bstream[b]));
         if (b < kNumBuckets) fb_em_kernel<true><<<bucketCount[b], kThreads, bucketSmem[b], c->bstream[b]>>>(prm, d_order + bucketBegin[b], bucketSmem[b]);
         else fb_em_kernel<false><<<bucketCount[b], kThreads, bucketSmem[b], c->bstream[b]>>>(prm, d_order + bucketBegin[b], bucketSmem[b]);
         CK(cudaGetLastError());
@@ -1460,6 +1474,10 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
     CK(cudaEventRecord(c->evDone, c->stream));
     CK(cudaEventSynchronize(c->evDone));
     float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    if (c->bucketStats) for (int b = 0; b <= kNumBuckets; b++) if (bucketCount[b]) {
+        float bm = 0; if (cudaEventElapsedTime(&bm, c->bev0[b], c->bev[b]) == cudaSuccess) c->bucketMs[b] += bm;
+        c->bucketItems[b] += bucketCount[b]; c->bucketLaunches[b]++;
+    }
     c->ctr.device_ms += ms; c->ctr.kernel_launches += launches; c->ctr.d2h_bytes += (int64_t)outTotal;
     if (c->device < 64) {
         DevClock& k = g_clock[c->device]; std::lock_guard<std::mutex> l(k.mu);

@@ -18,8 +18,10 @@
 #include <stdexcept>
 #include <thread>
 #include <time.h>
+#include <fcntl.h>
 #include <sys/mman.h>
 #include <ucontext.h>
+#include <unistd.h>
 
 #include "fb_gapfiller.h"
 #include "fb_io.h"
@@ -32,8 +34,8 @@ namespace fb {
 // fiber instead of blocking an OS thread, so thousands of gaps can be in flight on a handful of threads.
 // A worker owns its fibers for their whole life (no migration).  When all of a worker's fibers are parked it
 // hands their requests to the lane; the last worker to arrive flushes them as ONE fb_em_run, after which every
-// worker resumes its fibers and each fiber unpacks its own results from the pinned arena (which stays valid
-// until the next flush, and that needs every worker to arrive again).
+// worker resumes its fibers and each fiber reads its own results in place in the pinned arena (which stays valid
+// until the next flush, and that needs every worker -- hence this fiber -- to arrive again).
 // ---------------------------------------------------------------------------------------------------------
 struct Fiber {
     ucontext_t ctx, *ret = nullptr;
@@ -62,14 +64,9 @@ public:
             ItemResult& res = results.back(); const unsigned char* b = (const unsigned char*)h;
             res.calls = h->calls; res.compCount = h->comp_count; res.flags = h->flags; res.nReads = h->n_reads;
             res.candLen = h->cand_len; res.nSlots = h->n_slots; res.placements = h->placements;
-            const size_t n = (size_t)h->n_slots * h->n_reads;
-            const double* p1 = (const double*)(b + h->off_p1max); res.p1max.assign(p1, p1 + n);
-            const double* p2 = (const double*)(b + h->off_p2max); res.p2max.assign(p2, p2 + n);
-            const int32_t* ps = (const int32_t*)(b + h->off_pos2); res.pos2.assign(ps, ps + n);
-            res.soft.assign(b + h->off_soft, b + h->off_soft + h->cand_len);
-            res.hard.assign(b + h->off_hard, b + h->off_hard + h->cand_len);
-            const int32_t* cv = (const int32_t*)(b + h->off_cov); res.cov.assign(cv, cv + h->cand_len);
-            if (h->off_counts >= 0) { const double* c = (const double*)(b + h->off_counts); res.counts.assign(c, c + (size_t)5 * h->cand_len); }
+            res.p1max = (const double*)(b + h->off_p1max); res.p2max = (const double*)(b + h->off_p2max); res.pos2 = (const int32_t*)(b + h->off_pos2);
+            res.soft = b + h->off_soft; res.hard = b + h->off_hard; res.cov = (const int32_t*)(b + h->off_cov);
+            res.counts = h->off_counts >= 0 ? (const double*)(b + h->off_counts) : nullptr;
         }
         f->reqItems = nullptr;
     }
@@ -402,12 +399,23 @@ int fillgapsMain(int argc, const char* const* argv) {
     auto t4 = clk::now();
 
     // ---- outputs (gaps beyond the shorter of gapInfo/stat2 keep an empty entry, like a missing worker line)
-    if (!writeGapout(a.tmpDir + "gapout.txt", gaps, results)) { fprintf(stderr, "cannot write gapout.txt\n"); return 1; }
-    {
-        FILE* df = fopen((a.tmpDir + "draw.txt").c_str(), "w");
-        if (df) { for (auto& r : results) fputs(r.drawText.c_str(), df); fclose(df); }
+    {   // the three output files are independent: written side by side
+        bool okGapout = true, okFilled = true;
+        std::thread tg([&] { okGapout = writeGapout(a.tmpDir + "gapout.txt", gaps, results); });
+        std::thread td([&] {
+            const int fd = open((a.tmpDir + "draw.txt").c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+            if (fd < 0) return;
+            std::string buf; buf.reserve(8u << 20);
+            auto flushBuf = [&] { size_t off = 0; while (off < buf.size()) { ssize_t k = write(fd, buf.data() + off, buf.size() - off); if (k <= 0) break; off += (size_t)k; } buf.clear(); };
+            for (auto& r : results) { buf += r.drawText; if (buf.size() >= (4u << 20)) flushBuf(); }
+            flushBuf();
+            close(fd);
+        });
+        okFilled = writeFilledContigs(a.tmpDir, sc, gaps, results, totGaps);
+        tg.join(); td.join();
+        if (!okGapout) { fprintf(stderr, "cannot write gapout.txt\n"); return 1; }
+        if (!okFilled) { fprintf(stderr, "cannot write filledContigs.fa\n"); return 1; }
     }
-    if (!writeFilledContigs(a.tmpDir, sc, gaps, results, totGaps)) { fprintf(stderr, "cannot write filledContigs.fa\n"); return 1; }
     auto t5 = clk::now();
     rs.tLoad = secs(t0, t1); rs.tModel = modelSecs; rs.tPrep = secs(t2, t3); rs.tFill = secs(t3, t4); rs.tWrite = secs(t4, t5);
     for (auto& r : results) rs.refPlacements += r.refPlacements;

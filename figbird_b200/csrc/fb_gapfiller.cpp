@@ -381,7 +381,8 @@ void GapFill::initializeEffects(int Lg) {
     if (std::min(maxRightCi_, Lg) - 5 >= 100) pileUp(Lg, true);
 }
 
-void GapFill::setConcensus(const std::vector<uint8_t>& codes, int len) {
+void GapFill::setConcensus(const std::vector<uint8_t>& codes, int len) { setConcensus(codes.data(), len); }
+void GapFill::setConcensus(const uint8_t* codes, int len) {
     if ((int)concensus_.size() < len + 1) concensus_.resize(len + 1, 0);
     for (int i = 0; i < len; i++) concensus_[i] = letter(codes[i]);
     concensus_[len] = '\0';
@@ -535,9 +536,9 @@ void GapFill::borderUpdate(int Lg) {
 double GapFill::unmappedEpilogue(const ItemResult& r, int slot, int Lg, int finalizeFlag, int updateFlag, int ge) {
     const int R = numReads_;
     double like = 0;
-    const double* p1 = r.p1max.data() + (size_t)slot * R;
-    const double* p2 = r.p2max.data() + (size_t)slot * R;
-    const int32_t* ps = r.pos2.data() + (size_t)slot * R;
+    const double* p1 = r.p1max + (size_t)slot * R;
+    const double* p2 = r.p2max + (size_t)slot * R;
+    const int32_t* ps = r.pos2 + (size_t)slot * R;
     for (int q = 0; q < R; q++) {
         markAccepted_[q] = 0; finalReadpos_[q] = Pos3{-200, 0, -1};
         if (Lg == og_) unmPosOrg_[q] = Pos3{-200, 0, 0};
@@ -596,12 +597,14 @@ double GapFill::unmappedEpilogue(const ItemResult& r, int slot, int Lg, int fina
 }
 
 // detect_overlap_gapestimate (Figbird.cpp:2513-2779).  pflag rows: {used, position}.
-void GapFill::detectOverlap(const std::vector<std::array<int, 2>>& pflag, const std::vector<std::array<int, 3>>*, int gaplen, int* ret, int lenThresh) {
+void GapFill::detectOverlap(const std::vector<std::array<int, 2>>& pflag, const std::vector<std::array<int, 3>>*, int gaplen, int* ret, int lenThresh, bool* touchedSaved) {
     int lMax = -kMaxGap, rMin = kMaxGap;
-    std::vector<int> leftCross, rightCross;
+    std::vector<int>& leftCross = scratchLeft_; std::vector<int>& rightCross = scratchRight_;
+    leftCross.clear(); rightCross.clear();
     const int np = (int)std::min<size_t>(in_.partial.size(), 3001);
     const int prc = partialReadCount_;
-    std::vector<int> smFlag(prc, 0);
+    std::vector<int>& smFlag = scratchSm_; smFlag.assign(prc, 0);
+    if (touchedSaved) *touchedSaved = false;
     const double mismatchThreshold = .1;
     for (int p = 0; p < np && p < prc; p++) {
         if (pflag[p][0] == 0) continue;
@@ -638,6 +641,7 @@ void GapFill::detectOverlap(const std::vector<std::array<int, 2>>& pflag, const 
         return sub(s1, gaplen - placed, sideLimit_);
     };
     if (rMin <= lMax) {
+        if (touchedSaved) *touchedSaved = true;      // from here on partial_saved_read_temp is always written (set by a pair, or reset below)
         int maxOverlap = 0, falseFlag = 0;
         for (size_t i = 0; i < leftCross.size(); i++) for (size_t j = 0; j < rightCross.size(); j++) {
             const int li = leftCross[i], ri = rightCross[j];
@@ -672,27 +676,29 @@ void GapFill::detectOverlap(const std::vector<std::array<int, 2>>& pflag, const 
     ret[0] = 0; ret[1] = 0;
 }
 
-// partial-mode placeReads after the scored loops (Figbird.cpp:3258-3523), for one call
-double GapFill::partialEpilogue(const ItemResult& r, int slot, int Lg) {
+// partial-mode placeReads after the scored loops (Figbird.cpp:3258-3523), for one call.
+// savedOnly: apply nothing but the call's effect on partial_saved_read_temp (see evalCandidate).
+double GapFill::partialEpilogue(const ItemResult& r, int slot, int Lg, bool savedOnly, bool* touchedSaved) {
     const int R = (int)prep_.readLen.size();
-    const double* p1 = r.p1max.data() + (size_t)slot * R;
-    const double* p2 = r.p2max.data() + (size_t)slot * R;
-    const int32_t* ps = r.pos2.data() + (size_t)slot * R;
+    const double* p1 = r.p1max + (size_t)slot * R;
+    const double* p2 = r.p2max + (size_t)slot * R;
+    const int32_t* ps = r.pos2 + (size_t)slot * R;
     double like = 0;
-    for (int q = 0; q < R; q++) if (p1[q] > 0) like += log(p1[q]);
-    std::vector<std::array<int, 2>> pflag(partialReadCount_, std::array<int, 2>{{1, 0}});
-    if (Lg == og_) for (auto& o : partialPosOrg_) o = std::array<int, 3>{{0, -200, 0}};
+    if (!savedOnly) for (int q = 0; q < R; q++) if (p1[q] > 0) like += log(p1[q]);
+    std::vector<std::array<int, 2>>& pflag = scratchPflag_;
+    pflag.assign(partialReadCount_, std::array<int, 2>{{1, 0}});
+    if (Lg == og_ && !savedOnly) for (auto& o : partialPosOrg_) o = std::array<int, 3>{{0, -200, 0}};
     for (int q = 0; q < R; q++) {
         const double maxProb = p2[q] >= 0 ? p2[q] : -DBL_MAX;
         const double tlv = -log10(maxProb);
         if (tlv < m_.gapProbCutOff) {
-            validCount_++;
+            if (!savedOnly) validCount_++;
             pflag[q][1] = ps[q];
-            if (Lg == og_) partialPosOrg_[q] = std::array<int, 3>{{1, ps[q], prep_.readLen[q]}};
+            if (Lg == og_ && !savedOnly) partialPosOrg_[q] = std::array<int, 3>{{1, ps[q], prep_.readLen[q]}};
         } else pflag[q][0] = 0;
     }
     int ret[2] = {0, 0};
-    detectOverlap(pflag, nullptr, Lg, ret, 8);
+    detectOverlap(pflag, nullptr, Lg, ret, 8, touchedSaved);
     if (ret[0] == 300) like += ret[0];
     else if (ret[0] >= 1 && ret[0] < 200) like += 30 * ret[0];
     else if (ret[1] == -1) like += -100;
@@ -706,7 +712,14 @@ double GapFill::evalCandidate(const ItemResult& r, int Lg, int finalizeFlag) {
     refPlacements_ += r.placements;
     initializeEffects(Lg);
     if (prep_.mode == FB_MODE_PARTIAL) {
-        for (int s = 0; s < r.calls; s++) { validCount_ = 0; like = partialEpilogue(r, s, Lg); }
+        // The reference runs this epilogue after each of the three placeReads calls; what survives is the last call's likelihood,
+        // valid_count and original-length positions, and partial_saved_read_temp as the last call that *wrote* it left it
+        // (detect_overlap_gapestimate writes it exactly when it reaches its overlap block, Figbird.cpp:2671-2775).  So the last call
+        // is evaluated in full and earlier ones only while the saved pair is still undetermined.
+        bool touched = false;
+        validCount_ = 0;
+        like = partialEpilogue(r, r.calls - 1, Lg, false, &touched);
+        for (int s = r.calls - 2; s >= 0 && !touched; s--) partialEpilogue(r, s, Lg, true, &touched);
     } else {
         validCount_ = 0;
         like = unmappedEpilogue(r, 0, Lg, finalizeFlag, 0, r.calls - 1);
@@ -737,7 +750,7 @@ double GapFill::largeGapRounds(int Lg, int finalizeFlag, int updateFlag, bool) {
         if ((int)counts_.size() < Lg) counts_.resize(Lg, std::array<double, 5>{{0, 0, 0, 0, 0}});
         for (int x = 0; x < Lg; x++) for (int k = 0; k < 5; k++) counts_[x][k] = r.counts[(size_t)x * 5 + k];
         // comp_count bookkeeping mirrors the device: prev string changes only when the consensus changed
-        if (!(havePrev && prevHard == r.hard)) { prevHard = r.hard; havePrev = true; }
+        if (!(havePrev && (int)prevHard.size() == Lg && std::equal(prevHard.begin(), prevHard.end(), r.hard))) { prevHard.assign(r.hard, r.hard + Lg); havePrev = true; }
         validCount_ = 0;
         like = unmappedEpilogue(r, 0, Lg, finalizeFlag, updateFlag, i);
         // computeSequence(0,0) after the loop sees countsGap as the border update left it
@@ -757,7 +770,7 @@ double GapFill::runLength(int Lg, int finalizeFlag, int c) {
     std::vector<ItemResult> res;
     dev_->submit(bidx_, {s}, res);
     like = evalCandidate(res[0], Lg, finalizeFlag);
-    lastSoft_ = res[0].soft;
+    lastSoft_.assign(res[0].soft, res[0].soft + Lg);
     regionPerctMax_ = regionPerct_;
     return c == 0 ? (double)validCount_ : like;
 }
@@ -774,10 +787,10 @@ int GapFill::checkGapReads() {
     for (size_t i = 0; i < probes.size(); i++) {
         regionPerct_ = 0;
         evalCandidate(res[i], probes[i], 1);
-        lastSoft_ = res[i].soft;
+        lastSoft_.assign(res[i].soft, res[i].soft + probes[i]);
         // previous_str is a member that run() never resets (Figbird.cpp:3919-3927, 6254): the last probe's final hard consensus
         // is what the first placeReads call of the next evaluated length is compared with
-        prevStrLen_ = probes[i]; prevStr_ = res[i].hard;
+        prevStrLen_ = probes[i]; prevStr_.assign(res[i].hard, res[i].hard + probes[i]);
         regionPerctMax_ = regionPerct_;
         if (og_ < 30) { if (validCount_ > thresh) return -1; }
         else { if (validCount_ >= thresh) return -1; }
@@ -1161,7 +1174,7 @@ GapResult GapFill::run(DeviceQueue& dev, int batchGapIndex) {
                 initializeEffects(gapEstimate);
                 likelihood = unmappedEpilogue(r, 0, gapEstimate, 1, 0, r.calls - 1);
             } else likelihood = evalCandidate(r, gapEstimate, finalizeFlag);
-            lastSoft_ = r.soft;
+            lastSoft_.assign(r.soft, r.soft + gapEstimate);
         }
         setConcensus(lastSoft_, gapEstimate);          // computeSequence(0,0)
         gapLength_ = gapEstimate;

@@ -120,14 +120,16 @@ private:
     int hostMaxExt_ = -(1 << 30), hostMaxCi_ = -(1 << 30);
     std::vector<std::array<int, 4>> hostPileL_, hostPileR_;
     void setConcensus(const std::vector<uint8_t>& codes, int len);
+    void setConcensus(const uint8_t* codes, int len);
     void copyStr(std::vector<char>& dst, const std::vector<char>& src);
     ItemSpec emSpec(int Lg) const;
     double evalCandidate(const ItemResult& r, int Lg, int finalizeFlag);      // epilogue of the last call(s)
     double unmappedEpilogue(const ItemResult& r, int slot, int Lg, int finalizeFlag, int updateFlag, int ge);
-    double partialEpilogue(const ItemResult& r, int slot, int Lg);
+    double partialEpilogue(const ItemResult& r, int slot, int Lg, bool savedOnly = false, bool* touchedSaved = nullptr);
+    std::vector<std::array<int, 2>> scratchPflag_; std::vector<int> scratchLeft_, scratchRight_, scratchSm_;
     void borderUpdate(int Lg);
     double findOverlapUnmapped(int Lg);
-    void detectOverlap(const std::vector<std::array<int, 2>>& pflag3, const std::vector<std::array<int, 3>>* pflagFinal, int gaplen, int* ret, int lenThresh);
+    void detectOverlap(const std::vector<std::array<int, 2>>& pflag3, const std::vector<std::array<int, 3>>* pflagFinal, int gaplen, int* ret, int lenThresh, bool* touchedSaved = nullptr);
     double runLength(int Lg, int finalizeFlag, int c);        // GapFiller::run
     double largeGapRounds(int Lg, int finalizeFlag, int updateFlag, bool extraPass);
     int checkGapReads();

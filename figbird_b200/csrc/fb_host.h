@@ -87,14 +87,14 @@ struct GapResult {
 };
 
 // ---- device queue: batches EM/HARD items of many gaps into one fb_em_run (one per GPU)
-struct ItemResult {
+struct ItemResult {      // views into the engine's pinned result arena: valid until the owning gap submits its next request
     int calls = 0, compCount = 0, flags = 0, nReads = 0, candLen = 0, nSlots = 0;
     int64_t placements = 0;
-    std::vector<double> p1max, p2max;   // [slot][read]
-    std::vector<int32_t> pos2;
-    std::vector<uint8_t> soft, hard;
-    std::vector<int32_t> cov;
-    std::vector<double> counts;         // [row][5] or empty
+    const double* p1max = nullptr; const double* p2max = nullptr;   // [slot][read]
+    const int32_t* pos2 = nullptr;
+    const uint8_t* soft = nullptr; const uint8_t* hard = nullptr;    // [candLen]
+    const int32_t* cov = nullptr;
+    const double* counts = nullptr;     // [row][5] or null
 };
 
 class Engine;   // fb_engine.cpp

@@ -3,6 +3,13 @@
 #include <cctype>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <atomic>
+#include <thread>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "fb_host.h"
 #include "fb_io.h"
@@ -14,36 +21,74 @@ namespace fb {
 // exactly 1023 chars is kept whole -- even when its last char is the newline.  Scaffold lengths and hence
 // every coordinate depend on that, so the loader works on the same 1023-char chunks.
 bool loadScaffolds(const std::string& path, Scaffolds& out) {
-    FILE* f = fopen(path.c_str(), "r");
-    if (!f) return false;
-    std::string text;
-    { char buf[1 << 16]; size_t n; while ((n = fread(buf, 1, sizeof buf, f)) > 0) text.append(buf, n); }
-    fclose(f);
+    const int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    struct stat stt;
+    if (fstat(fd, &stt) != 0) { close(fd); return false; }
+    const size_t total = (size_t)stt.st_size;
+    const char* text = nullptr; void* mapped = nullptr; std::string owned;
+    if (total > 0) {
+        mapped = mmap(nullptr, total, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (mapped != MAP_FAILED) text = (const char*)mapped;
+        else { mapped = nullptr; owned.resize(total); size_t off = 0; while (off < total) { ssize_t k = pread(fd, &owned[off], total - off, (off_t)off); if (k <= 0) break; off += (size_t)k; } if (off != total) { close(fd); return false; } text = owned.data(); }
+    }
+    close(fd);
+    // Pass 1 (sequential, per physical line, no copying): which bytes go to which scaffold.  A chunk that starts with '>' is a
+    // header, one that starts with ';' is skipped; a sequence chunk shorter than 1023 chars loses its last char.
+    struct Seg { const char* p; size_t n; };
+    std::vector<std::vector<Seg>> segs(1);
+    std::vector<char> pushed(1, 0);        // the reference pushes a finished scaffold only when it is non-empty, and the last one always
     const size_t CH = 1023;
-    std::string cur;
+    size_t curLen = 0;
+    auto addSeg = [&](const char* p, size_t n) { if (n) { auto& v = segs.back(); if (!v.empty() && v.back().p + v.back().n == p) v.back().n += n; else v.push_back(Seg{p, n}); curLen += n; } };
     size_t p = 0;
-    while (p < text.size()) {
-        size_t e = text.find('\n', p);
-        size_t lineEnd = e == std::string::npos ? text.size() : e + 1;   // physical line incl. '\n'
-        for (size_t c = p; c < lineEnd; c += CH) {
-            size_t n = std::min(CH, lineEnd - c);
-            const char* chunk = text.data() + c;
+    while (p < total) {
+        const char* e = (const char*)memchr(text + p, '\n', total - p);
+        const size_t lineEnd = e ? (size_t)(e - text) + 1 : total;   // physical line incl. '\n'
+        const size_t n = lineEnd - p;
+        bool special = false;      // any chunk of this line starts with '>' or ';'
+        for (size_t c = p; c < lineEnd; c += CH) if (text[c] == '>' || text[c] == ';') { special = true; break; }
+        if (!special) addSeg(text + p, (n % CH) == 0 ? n : n - 1);
+        else for (size_t c = p; c < lineEnd; c += CH) {
+            const size_t m = std::min(CH, lineEnd - c);
+            const char* chunk = text + c;
             if (chunk[0] == ';') continue;
             if (chunk[0] == '>') {
-                std::string nm(chunk + 1, n >= 2 ? n - 2 : 0);          // drop '>' and the last char
+                std::string nm(chunk + 1, m >= 2 ? m - 2 : 0);          // drop '>' and the last char
                 size_t a = nm.find_first_not_of(" \t\n"), b = a == std::string::npos ? a : nm.find_first_of(" \t\n", a);
                 out.names.push_back(a == std::string::npos ? std::string() : nm.substr(a, b == std::string::npos ? b : b - a));
-                if (!cur.empty()) { out.seq.push_back(cur); cur.clear(); }
-            } else {
-                if (n < CH) cur.append(chunk, n - 1); else cur.append(chunk, n);
-            }
+                if (curLen > 0) { pushed.back() = 1; segs.emplace_back(); pushed.push_back(0); curLen = 0; }
+            } else addSeg(chunk, m < CH ? m - 1 : m);
         }
         p = lineEnd;
     }
-    out.seq.push_back(cur);
+    pushed.back() = 1;
+    // Pass 2 (parallel): copy + toupper() of the C locale (the reference never calls setlocale)
+    const size_t nS = segs.size();
+    out.seq.assign(nS, std::string());
+    struct Job { size_t s; size_t dst; const char* p; size_t n; };
+    std::vector<Job> jobs;
     out.totalLength = 0;
-    // toupper() of the C locale (the reference never calls setlocale), as a loop the compiler vectorises
-    for (auto& s : out.seq) { char* d = &s[0]; const size_t n = s.size(); for (size_t i = 0; i < n; i++) { const char ch = d[i]; d[i] = (ch >= 'a' && ch <= 'z') ? (char)(ch - 32) : ch; } out.totalLength += (long)n; }
+    const size_t BLK = 4u << 20;
+    for (size_t i = 0; i < nS; i++) {
+        size_t len = 0; for (auto& g : segs[i]) len += g.n;
+        out.seq[i].resize(len);
+        out.totalLength += (long)len;
+        size_t d = 0;
+        for (auto& g : segs[i]) { for (size_t o = 0; o < g.n; o += BLK) jobs.push_back(Job{i, d + o, g.p + o, std::min(BLK, g.n - o)}); d += g.n; }
+    }
+    auto runJob = [&](const Job& j) { char* d = &out.seq[j.s][j.dst]; const char* sp = j.p; for (size_t i = 0; i < j.n; i++) { const char ch = sp[i]; d[i] = (ch >= 'a' && ch <= 'z') ? (char)(ch - 32) : ch; } };
+    int nt = (int)std::thread::hardware_concurrency();
+    if (const char* e2 = getenv("FIGBIRD_HOST_THREADS")) nt = atoi(e2);
+    nt = std::max(1, std::min(nt, (int)((out.totalLength >> 22) + 1)));
+    if (nt <= 1) for (auto& j : jobs) runJob(j);
+    else {
+        std::atomic<size_t> next(0);
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) th.emplace_back([&] { for (size_t i; (i = next++) < jobs.size();) runJob(jobs[i]); });
+        for (auto& t : th) t.join();
+    }
+    if (mapped) munmap(mapped, total);
     return true;
 }
 
@@ -171,6 +216,7 @@ bool writeFilledContigs(const std::string& tmpDir, const Scaffolds& sc, const st
     FILE* out = fopen((tmpDir + "filledContigs.fa").c_str(), "w");
     FILE* nf = fopen((tmpDir + "Ncount.txt").c_str(), "w");
     if (!out || !nf) { if (out) fclose(out); if (nf) fclose(nf); return false; }
+    std::vector<char> iobuf(8u << 20); setvbuf(out, iobuf.data(), _IOFBF, iobuf.size());
     std::vector<int> gtf(std::max(totGaps, (int)gaps.size()) + 1, 0);
     for (size_t i = 0; i < res.size(); i++) gtf[i] = res[i].gapToFill;
     int gapCount = -1; size_t nextEntry = 0;
@@ -201,8 +247,8 @@ bool writeFilledContigs(const std::string& tmpDir, const Scaffolds& sc, const st
                         nextEntry++;
                     }
                     for (char ch : gapString) if (ch == 'N') newNcount++;
-                    fputs(buf.c_str(), out);
-                    if (gapStringLength > 0) fputs(gapString.c_str(), out);
+                    fwrite(buf.data(), 1, buf.size(), out);
+                    if (gapStringLength > 0) fwrite(gapString.data(), 1, gapString.size(), out);
                     buf.clear();
                     nStart = 0;
                 }
@@ -210,7 +256,7 @@ bool writeFilledContigs(const std::string& tmpDir, const Scaffolds& sc, const st
                 else buf.push_back(s[j]);
             }
         }
-        fprintf(out, "%s\n", buf.c_str());
+        fwrite(buf.data(), 1, buf.size(), out); fputc('\n', out);
     }
     fprintf(nf, "%d", newNcount == 0 ? 0 : 1);
     fclose(out); fclose(nf);
