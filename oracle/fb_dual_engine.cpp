@@ -46,6 +46,12 @@ bool init() {
     return ok == 1;
 }
 long g_mismatch = 0, g_items = 0;
+double g_worst = 0;      // largest relative deviation of a count-matrix entry (per-position base weight) seen so far
+// Summary for the tests: written at process exit (engine contexts are pooled by the host program and never destroyed)
+struct Summary { ~Summary() {
+    if (const char* p = getenv("FB_DUAL_SUMMARY")) { FILE* f = fopen(p, "w"); if (f) { fprintf(f, "{\"items\": %ld, \"mismatching\": %ld, \"worst_weight_rel\": %.3e}\n", g_items, g_mismatch, g_worst); fclose(f); } }
+    fprintf(stderr, "fb_dual: %ld items compared, %ld mismatching, worst relative weight deviation %.3e\n", g_items, g_mismatch, g_worst);
+} } g_summary;
 }  // namespace
 
 struct fb_ctx { fb_ctx* d; fb_ctx* o; std::string err; int cutoff = 0; };
@@ -63,7 +69,6 @@ extern "C" void fb_ctx_destroy(fb_ctx* c) {
     if (!c) return;
     if (c->d) dev().ctx_destroy(c->d);
     if (c->o) ora().ctx_destroy(c->o);
-    fprintf(stderr, "fb_dual: %ld items compared, %ld mismatching\n", g_items, g_mismatch);
     delete c;
 }
 extern "C" const char* fb_last_error(const fb_ctx* c) { return c ? (c->err.empty() ? dev().last_error(c->d) : c->err.c_str()) : "null"; }
@@ -126,6 +131,7 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items_in, int32_t n,
             if (memcmp(a + A->off_cov, b + B->off_cov, sizeof(int32_t) * Lg)) why += " cov";
             if (A->off_counts >= 0 && B->off_counts >= 0) {
                 const double* ac = (const double*)(a + A->off_counts); const double* bc = (const double*)(b + B->off_counts);
+                for (int k = 0; k < 5 * Lg; k++) if (ac[k] != 0) { const double rel = fabs(ac[k] - bc[k]) / fabs(ac[k]); if (rel > g_worst) g_worst = rel; }
                 for (int k = 0; k < 5 * Lg; k++) if (fabs(ac[k] - bc[k]) > 1e-5 * fabs(ac[k])) {
                     char buf[200]; snprintf(buf, sizeof buf, " counts[row %d col %d] oracle %.17g device %.17g", k / 5, k % 5, ac[k], bc[k]);
                     if (why.empty()) { countsOnly = true; } why += buf; break; }

@@ -42,8 +42,12 @@ def test_product_library_has_no_cpu_engine_symbols():
     """The oracle engine must not be linked into the product (no CPU fallback)."""
     import subprocess
     out = subprocess.run(["nm", "-D", "--defined-only", LIBS["product"]], stdout=subprocess.PIPE).stdout.decode()
-    assert "fb_em_kernel" in subprocess.run(["cuobjdump", "-elf", LIBS["product"]], stdout=subprocess.PIPE, stderr=subprocess.STDOUT).stdout.decode() or True
     assert "oracle" not in out.lower()
+    # ... and it does carry the sm_100a kernels
+    sass = subprocess.run(["cuobjdump", "-lelf", LIBS["product"]], stdout=subprocess.PIPE, stderr=subprocess.STDOUT).stdout.decode()
+    assert "sm_100a" in sass, sass[-500:]
+    syms = subprocess.run(["nm", LIBS["product"]], stdout=subprocess.PIPE).stdout.decode()
+    assert "fb_em_kernel" in syms and "fb_flank_kernel" in syms
 
 
 def test_product_fails_loudly_without_gpu():

@@ -30,6 +30,24 @@ def test_product_matches_reference_golden(case, mode):
     assert m["ref_placements_p1"] == json.load(open(os.path.join(gu.GOLDEN, "placements.json")))[os.path.basename(case)][mode]
 
 
+@pytest.mark.parametrize("mode", ["partial", "unmapped"])
+def test_device_weights_item_by_item_on_real_inputs(case, mode):
+    """The host program on the dual engine (oracle/fb_dual_engine.cpp): every work item of a real run goes to the CUDA library
+    and to the CPU oracle; discrete results must be identical, pass-2 products bit-exact, and every per-position base
+    weight (countsGap entry) within 1e-5 relative -- BASELINE's bar -- with the files still byte-identical to the reference."""
+    import json
+    summary = os.path.join(case, "dual_%s.json" % mode)
+    env = {"FB_DUAL_DEVICE_LIB": os.path.join(fc.PBUILD, "libfigbird_b200.so"), "FB_DUAL_ORACLE_LIB": os.path.join(fc.OBUILD, "libfb_oracle.so"),
+           "FB_DUAL_SUMMARY": summary, "FB_ORACLE_THREADS": "8"}
+    o = fc.run_ours(case, mode, os.path.join(fc.OBUILD, "fillgaps_dual"), extra_env=env, name="dual")
+    exp = gu.expected(case, mode)
+    for f in ("gapout.txt", "filledContigs.fa", "Ncount.txt", "draw.txt"):
+        assert o[f] == exp[f], f
+    s = json.load(open(summary))
+    assert s["items"] > 0 and s["mismatching"] == 0, (s, o["log"][-3000:])
+    assert s["worst_weight_rel"] <= 1e-5, s
+
+
 def test_in_process_entry_point(case):
     from figbird_b200 import capi
     run = os.path.join(case, "run_inproc")
@@ -88,10 +106,12 @@ def test_c1_against_live_reference(big_case):
     """Full BASELINE configs[0] differential check (reference runs with numthreads=4 as the config says)."""
     if os.environ.get("FB_SKIP_LIVE_REF"):
         pytest.skip("disabled")
-    r = fc.run_reference(big_case, "partial", threads=4)
-    o = fc.run_ours(big_case, "partial", fc.product_exe(), name="live")
-    for f in ("gapout.txt", "filledContigs.fa", "Ncount.txt"):
-        assert r[f] == o[f], f
+    for mode in ("partial", "unmapped"):
+        r = fc.run_reference(big_case, mode, threads=4)
+        o = fc.run_ours(big_case, mode, fc.product_exe(), name="live")
+        for f in ("gapout.txt", "filledContigs.fa", "Ncount.txt"):
+            assert r[f] == o[f], (mode, f)
+        assert fc.draw_by_gap(r["draw.txt"]) == fc.draw_by_gap(o["draw.txt"]), mode
 
 
 def test_c2_full_size_against_reference_golden(tmp_path_factory):
