@@ -78,7 +78,13 @@ namespace {
 #ifndef FB_PREF
 #define FB_PREF 1       // 1: integer mismatch prefilter in front of the pass-2 products
 #endif
+#ifndef FB_THREADS_BIG
+#define FB_THREADS_BIG 512
+#endif
 constexpr int kThreads = FB_THREADS;
+constexpr int kThreadsBig = FB_THREADS_BIG;
+constexpr int kMaxReadLen = 255;          // read lengths travel in 8 bits (RMeta::packed); one limit for the model and the batch
+constexpr int kBigBucket = 3;             // first shared-memory bucket that leaves room for one CTA per SM only
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxSmem = 200 * 1024;      // dynamic shared memory we opt in to (227 KB is the sm_100 limit)
 constexpr int kChunkWant = 72 * 1024;     // weights + read-code staging we ask for per CTA when the reads allow it
@@ -143,7 +149,7 @@ __host__ __device__ inline Plan makePlan(int Lg, int F, int modelLen, int maxLen
     p.oG = o; o += al16(p.rows);
     p.oPREV = o; o += al16(Lg);
     p.tableBytes = al16(o);
-    if (p.tableBytes < 12 * kThreads) p.tableBytes = al16(12 * kThreads);     // the prologue's prefix-sum scratch lives here
+    if (p.tableBytes < 12 * kThreadsBig) p.tableBytes = al16(12 * kThreadsBig);     // the prologue's prefix-sum scratch lives here
     o = 0;
     p.oME = o; o += al16(8 * modelLen);
     p.oMER = o; o += al16(8 * modelLen);
@@ -296,8 +302,11 @@ __global__ void __launch_bounds__(128) fb_flank_kernel(const Params prm, int nRe
     }
 }
 
-template <bool TSMEM>
-__global__ void __launch_bounds__(kThreads, TSMEM ? FB_CTAS : 1) fb_em_kernel(const Params prm, const int* __restrict__ order, const int smemBytes) {
+// NT threads per CTA: kThreads (2 CTAs per SM) for items whose shared memory lets two CTAs share an SM, kThreadsBig for the buckets
+// that leave room for one CTA only (long candidates: the same number of warps per SM then works on one item).
+template <bool TSMEM, int NT>
+__global__ void __launch_bounds__(NT, (TSMEM && NT == FB_THREADS) ? FB_CTAS : 1) fb_em_kernel(const Params prm, const int* __restrict__ order, const int smemBytes) {
+    constexpr int kThreads = NT, kWarps = NT / 32;
     const DevItem it = prm.items[order[blockIdx.x]];
     const DevGap g = prm.gaps[it.gap];
     const DevModel& m = prm.m;
@@ -1167,8 +1176,9 @@ extern "C" fb_status fb_ctx_create(int32_t device, fb_ctx** out) {
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
     CK(cudaEventCreateWithFlags(&c->evDone, cudaEventBlockingSync | cudaEventDisableTiming));
-    CK(cudaFuncSetAttribute(fb_em_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CK(cudaFuncSetAttribute(fb_em_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CK(cudaFuncSetAttribute(fb_em_kernel<true, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CK(cudaFuncSetAttribute(fb_em_kernel<true, kThreadsBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CK(cudaFuncSetAttribute(fb_em_kernel<false, kThreadsBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     c->bucketStats = getenv("FIGBIRD_BUCKET_STATS") != nullptr;
     for (int b = 0; b <= kNumBuckets; b++) {
         CK(cudaStreamCreateWithFlags(&c->bstream[b], cudaStreamNonBlocking));
@@ -1208,9 +1218,12 @@ template <class T> static fb_status upload(fb_ctx* c, DevBuf<T>& b, const T* src
 }
 
 extern "C" fb_status fb_model_upload(fb_ctx* c, const FbModel* m) {
-    if (!c || !m || m->max_read_len <= 0 || m->n_insert <= 0) return FB_ERR_ARG;
+    if (!c || !m || m->max_read_len <= 0 || m->n_insert <= 0 || !m->err_pos || !m->ins_pos || !m->del_pos || !m->insert_pdf) return FB_ERR_ARG;
+    // every argument check comes before the first mutation: a rejected upload leaves the context as it was
+    if (m->max_read_len > kMaxReadLen) { c->err = "reads longer than 255 bases are not supported by this build"; return FB_ERR_ARG; }
     CK(cudaSetDevice(c->device));
     const int RL = m->max_read_len;
+    c->haveModel = false;
     std::vector<double> match(RL);
     bool prunable = true;      // every pass-2 factor in [0, 1] => running products only fall (pass-2 pruning is exact)
     for (int k = 0; k < RL; k++) {
@@ -1250,7 +1263,6 @@ extern "C" fb_status fb_model_upload(fb_ctx* c, const FbModel* m) {
         }
         if (m->prob_cutoff <= 0) c->dm.accept_min_p = INFINITY;   // -log10(p) < 0 needs p > 1: never for a probability
     }
-    if (RL > 256) { c->err = "reads longer than 256 bases are not supported by this build"; return FB_ERR_ARG; }
     for (int k = 0; k < RL; k++) { c->hEtab[k] = m->err_pos[k]; c->hEtab[256 + (RL - 1 - k)] = m->err_pos[k]; }
     c->haveModel = true; c->flankDirty = true;
     return FB_OK;
@@ -1261,8 +1273,20 @@ extern "C" fb_status fb_batch_upload(fb_ctx* c, const FbGapBatch* b) {
     CK(cudaSetDevice(c->device));
     c->hGaps.resize(b->n_gaps); c->hGapMaxLen.assign(b->n_gaps, 1);
     std::vector<int> readGap((size_t)std::max(b->n_reads, 1), -1);
+    if (b->n_reads < 0 || b->n_codes < 0 || b->n_flank < 0 || b->n_pile_rows < 0 || (b->n_gaps > 0 && !b->gaps)) return FB_ERR_ARG;
+    {   // reads must not share code bytes (the per-read flank products are written at 2 x read_code_off)
+        bool ascending = true;
+        for (int q = 0; q + 1 < b->n_reads && ascending; q++) if (b->read_code_off[q + 1] < b->read_code_off[q] + b->read_len[q]) ascending = false;
+        if (!ascending) {
+            std::vector<int> ord(b->n_reads); for (int q = 0; q < b->n_reads; q++) ord[q] = q;
+            std::sort(ord.begin(), ord.end(), [&](int x, int y) { return b->read_code_off[x] < b->read_code_off[y]; });
+            for (int k = 0; k + 1 < b->n_reads; k++) if (b->read_code_off[ord[k + 1]] < b->read_code_off[ord[k]] + b->read_len[ord[k]]) { c->err = "read_code_off ranges overlap"; return FB_ERR_ARG; }
+        }
+    }
     for (int i = 0; i < b->n_gaps; i++) {
         const FbGap& g = b->gaps[i];
+        if (g.mode != FB_MODE_PARTIAL && g.mode != FB_MODE_UNMAPPED) { c->err = "bad gap mode"; return FB_ERR_ARG; }
+        if (g.n_reads < 0 || g.flank_len < 0 || g.pile_len < 0 || g.pile_begin < 0 || (long long)g.pile_begin + g.pile_len > b->n_pile_rows) { c->err = "pile-up rows out of range"; return FB_ERR_ARG; }
         DevGap d{}; d.gap_start = g.gap_start; d.mode = g.mode; d.orig_len = g.orig_len; d.n_reads = g.n_reads; d.read_begin = g.read_begin;
         d.flank_len = g.flank_len; d.flank_begin = g.flank_begin; d.pile_len = g.pile_len; d.pile_begin = g.pile_begin;
         c->hGaps[i] = d;
@@ -1273,7 +1297,8 @@ extern "C" fb_status fb_batch_upload(fb_ctx* c, const FbGapBatch* b) {
             if (b->read_code_off[g.read_begin + q] < 0 || b->read_code_off[g.read_begin + q] + len > b->n_codes) { c->err = "read codes out of range"; return FB_ERR_ARG; }
             readGap[g.read_begin + q] = i;
             if (len > g.flank_len + 1) { c->err = "flank_len must be >= read length - 1"; return FB_ERR_ARG; }
-            if (len > 255) { c->err = "read longer than 255 bases"; return FB_ERR_ARG; }
+            if (len < 0 || len > kMaxReadLen) { c->err = "read length outside [0, 255]"; return FB_ERR_ARG; }
+            if ((int)b->read_jlo[g.read_begin + q] + (int)b->read_jcut[g.read_begin + q] > len) { c->err = "read_jlo + read_jcut exceeds the read length"; return FB_ERR_ARG; }
             ml = len > ml ? len : ml;
         }
         c->hGapMaxLen[i] = ml;
@@ -1357,6 +1382,9 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
     for (int i = 0; i < n; i++) {
         const FbWorkItem& it = items[i];
         if (it.gap < 0 || it.gap >= (int)c->hGaps.size() || it.cand_len < 0 || it.cand_len > 60000) { c->err = "bad work item"; return FB_ERR_ARG; }
+        if (it.kind != FB_ITEM_EM && it.kind != FB_ITEM_HARD) { c->err = "bad work item kind"; return FB_ERR_ARG; }
+        if (it.max_rounds < 0 || it.max_rounds > 100000) { c->err = "max_rounds outside [0, 100000]"; return FB_ERR_ARG; }
+        if (it.kind == FB_ITEM_EM && (it.flags & FB_FLAG_RECORD_ALL) && it.max_rounds + ((it.flags & FB_FLAG_EXTRA_PASS) ? 1 : 0) == 0) { c->err = "RECORD_ALL item without a call to record"; return FB_ERR_ARG; }
         const DevGap& g = c->hGaps[it.gap];
         DevItem d{};
         d.kind = it.kind; d.gap = it.gap; d.Lg = it.cand_len; d.max_rounds = it.max_rounds; d.flags = it.flags; d.comp_in = it.comp_count_in;
@@ -1460,8 +1488,9 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
         if (!bucketCount[b]) continue;
         CK(cudaStreamWaitEvent(c->bstream[b], c->ev0, 0));
         if (c->bucketStats) CK(cudaEventRecord(c->bev0[b], c->bstream[b]));
-        if (b < kNumBuckets) fb_em_kernel<true><<<bucketCount[b], kThreads, bucketSmem[b], c->bstream[b]>>>(prm, d_order + bucketBegin[b], bucketSmem[b]);
-        else fb_em_kernel<false><<<bucketCount[b], kThreads, bucketSmem[b], c->bstream[b]>>>(prm, d_order + bucketBegin[b], bucketSmem[b]);
+        if (b < kBigBucket) fb_em_kernel<true, kThreads><<<bucketCount[b], kThreads, bucketSmem[b], c->bstream[b]>>>(prm, d_order + bucketBegin[b], bucketSmem[b]);
+        else if (b < kNumBuckets) fb_em_kernel<true, kThreadsBig><<<bucketCount[b], kThreadsBig, bucketSmem[b], c->bstream[b]>>>(prm, d_order + bucketBegin[b], bucketSmem[b]);
+        else fb_em_kernel<false, kThreadsBig><<<bucketCount[b], kThreadsBig, bucketSmem[b], c->bstream[b]>>>(prm, d_order + bucketBegin[b], bucketSmem[b]);
         CK(cudaGetLastError());
         CK(cudaEventRecord(c->bev[b], c->bstream[b]));
         CK(cudaStreamWaitEvent(c->stream, c->bev[b], 0));

@@ -197,8 +197,14 @@ static void parallelFor(int n, int threads, F f) {
     threads = std::max(1, std::min(threads, n));
     std::atomic<int> next(0);
     std::vector<std::thread> th;
-    for (int t = 0; t < threads; t++) th.emplace_back([&] { for (int i; (i = next++) < n;) f(i); });
+    std::mutex emu; std::string error; bool failed = false;
+    for (int t = 0; t < threads; t++) th.emplace_back([&] {
+        try { for (int i; (i = next++) < n;) f(i); }
+        catch (const std::exception& e) { std::lock_guard<std::mutex> l(emu); if (!failed) { failed = true; error = e.what(); } next = n; }
+        catch (...) { std::lock_guard<std::mutex> l(emu); if (!failed) { failed = true; error = "worker failed"; } next = n; }
+    });
     for (auto& t : th) t.join();
+    if (failed) throw std::runtime_error(error);      // rethrown on the caller's thread (fb_fillgaps_main turns it into exit status 1)
 }
 
 // Engine contexts survive fb_fillgaps_main: an in-process caller (one FillGaps call per pipeline iteration) pays stream /
@@ -382,6 +388,7 @@ int fillgapsMain(int argc, const char* const* argv) {
         });
         for (auto& t : th) t.join();
         if (!lw.error.empty()) devErr[d] = lw.error;
+        if (!devErr[d].empty()) { fb_ctx_destroy(ctx); return; }      // a CUDA error is sticky: never pool a context that has failed
         devWork[d] = secs(d1, clk::now()); devCpu[d] = cpuNs.load() * 1e-9;
         {   // this run's share of the context's cumulative counters
             FbCounters c1{}; fb_get_counters(ctx, &c1);

@@ -222,4 +222,5 @@ def draw_by_gap(data):
         cur.append(line)
     if key is not None:
         out[key] = b"\n".join(cur)
-    return out
+    # (the text of a gap ends with a newline; where it ends, relative to the next gap's header or the end of the file, differs with the order)
+    return {k: v.rstrip(b"\n") for k, v in out.items()}
