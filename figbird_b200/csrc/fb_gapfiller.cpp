@@ -100,8 +100,9 @@ void GapFill::prepare() {
     bestString_.assign(maxGap + 1, 0);
     originalStr_.assign(og_ + 1, 0);
     gapCoverage_.assign(maxGap, 0);
-    counts_.assign(maxGap, std::array<double, 5>{{0, 0, 0, 0, 0}});
-    qualGap_.assign(maxGap, std::array<double, 5>{{0, 0, 0, 0, 0}});
+    // countsGap / qual_gap host copies (maxGap rows of 5 doubles each) are allocated where they are first used (large-gap rounds,
+    // finalize): most gaps never need them before finalize, and 10^4 gaps x 2 tables x 40 B x maxGap is gigabytes
+    counts_.clear(); qualGap_.clear();
     markAccepted_.assign(numReads_, 0); savedReads_.assign(numReads_, 0); mlvNonZero_.assign(numReads_, 0);
     finalReadpos_.assign(numReads_, Pos3{-200, 0, -1}); unmPosOrg_.assign(numReads_, Pos3{-200, 0, 0});
     partialPosOrg_.assign(partialReadCount_, std::array<int, 3>{{0, -200, 0}});
@@ -954,7 +955,7 @@ void GapFill::finalize(int gl) {
     }
     if (a_.partialFlag) {
         drawHeader(gapLength_);
-        for (auto& qg : qualGap_) qg = std::array<double, 5>{{0, 0, 0, 0, 0}};
+        qualGap_.assign(std::max(allocArg_, 1), std::array<double, 5>{{0, 0, 0, 0, 0}});
         for (int q = 0; q < R; q++) {
             const PartialRead& p = in_.partial[q];
             const int len = prep_.readLen[q];
@@ -1246,8 +1247,11 @@ GapResult GapFill::run(DeviceQueue& dev, int batchGapIndex) {
     out.gapStringLength = gapLength_;
     out.gapString.assign(concensus_.data(), strnlen(concensus_.data(), (size_t)gapLength_));   // printed with %s
     out.gapToFill = 0;
-    out.drawText = draw_;
+    out.drawText.swap(draw_);
     out.refPlacements = refPlacements_;
+    // the per-gap working set is not needed once the result is out
+    std::vector<std::array<double, 5>>().swap(counts_); std::vector<std::array<double, 5>>().swap(qualGap_);
+    std::vector<std::vector<double>>().swap(partialQuality_);
     return out;
 }
 

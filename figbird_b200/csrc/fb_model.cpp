@@ -19,6 +19,9 @@
 #include <memory>
 #include <thread>
 #include <unistd.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "fb_host.h"
 
@@ -321,9 +324,25 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err, 
             }
             const int strand = (fl.flag & 16) >> 4;
             const int readLength = fl.seqLen;
-            {   // (independent counters instead of one increment chain through memory)
+            {   // base composition of the read: 16 bases per step (byte compares, per-byte counters summed at the end)
                 long nA = 0, nC = 0, nG = 0, nT = 0;
-                for (int i = 0; i < readLength; i++) { const char c = fl.seq[i]; nA += c == 'A'; nC += c == 'C'; nG += c == 'G'; nT += c == 'T'; }
+                int i = 0;
+#if defined(__SSE2__)
+                const __m128i vA = _mm_set1_epi8('A'), vC = _mm_set1_epi8('C'), vG = _mm_set1_epi8('G'), vT = _mm_set1_epi8('T');
+                while (i + 16 <= readLength) {
+                    __m128i aA = _mm_setzero_si128(), aC = aA, aG = aA, aT = aA;
+                    const int stop = std::min(readLength - 15, i + 16 * 255);      // a byte counter holds 255 steps
+                    for (; i < stop; i += 16) {
+                        const __m128i v = _mm_loadu_si128((const __m128i*)(fl.seq + i));
+                        aA = _mm_sub_epi8(aA, _mm_cmpeq_epi8(v, vA)); aC = _mm_sub_epi8(aC, _mm_cmpeq_epi8(v, vC));
+                        aG = _mm_sub_epi8(aG, _mm_cmpeq_epi8(v, vG)); aT = _mm_sub_epi8(aT, _mm_cmpeq_epi8(v, vT));
+                    }
+                    const __m128i z = _mm_setzero_si128();
+                    auto hsum = [&](__m128i a) { const __m128i sd = _mm_sad_epu8(a, z); return (long)_mm_cvtsi128_si64(sd) + (long)_mm_cvtsi128_si64(_mm_srli_si128(sd, 8)); };
+                    nA += hsum(aA); nC += hsum(aC); nG += hsum(aG); nT += hsum(aT);
+                }
+#endif
+                for (; i < readLength; i++) { const char c = fl.seq[i]; nA += c == 'A'; nC += c == 'C'; nG += c == 'G'; nT += c == 'T'; }
                 st.baseCounts[0] += nA; st.baseCounts[1] += nC; st.baseCounts[2] += nG; st.baseCounts[3] += nT; st.baseCounts[4] += readLength - nA - nC - nG - nT;
             }
             if (readLength > RL) { st.uniqueMappedReads++; return; }
