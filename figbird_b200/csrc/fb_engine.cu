@@ -39,6 +39,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -1136,6 +1137,7 @@ struct fb_ctx {
     cudaEvent_t bev0[kNumBuckets + 1] = {};      // diagnostics (FIGBIRD_BUCKET_STATS): start of each bucket's launch
     double bucketMs[kNumBuckets + 1] = {}; long long bucketItems[kNumBuckets + 1] = {}, bucketLaunches[kNumBuckets + 1] = {};
     bool bucketStats = false;
+    double hostPrepS = 0, hostWaitS = 0, hostPostS = 0; long long hostItems = 0;      // diagnostics: wall seconds of fb_em_run's host phases
     int smemOptin = 0;
     bool haveModel = false, haveBatch = false;
     DevModel dm{};
@@ -1149,6 +1151,7 @@ struct fb_ctx {
     DevBuf<unsigned long long> d_ctr;
     unsigned char* h_out = nullptr; size_t h_out_cap = 0;     // pinned result arena
     unsigned char* h_in = nullptr; size_t h_in_cap = 0;       // pinned staging for items + inputs
+    unsigned long long* h_ctr = nullptr;                      // pinned copy of the device counters (a pageable target would make the copy -- and the host thread -- wait spinning)
     FbCounters ctr{};
     double hEtab[512] = {};        // host copy of Params::e_tab
 };
@@ -1186,6 +1189,7 @@ extern "C" fb_status fb_ctx_create(int32_t device, fb_ctx** out) {
         else CK(cudaEventCreateWithFlags(&c->bev[b], cudaEventDisableTiming));
     }
     CK(c->d_ctr.ensure(32)); CK(cudaMemset(c->d_ctr.p, 0, 32 * sizeof(unsigned long long)));
+    CK(cudaMallocHost((void**)&c->h_ctr, 32 * sizeof(unsigned long long))); memset(c->h_ctr, 0, 32 * sizeof(unsigned long long));
     if (device < 64) {
         DevClock& k = g_clock[device]; std::lock_guard<std::mutex> l(k.mu);
         if (!k.epoch) { CK(cudaEventCreate(&k.epoch)); CK(cudaEventRecord(k.epoch, c->stream)); CK(cudaEventSynchronize(k.epoch)); }
@@ -1203,6 +1207,7 @@ extern "C" void fb_ctx_destroy(fb_ctx* c) {
     c->d_items.release(); c->d_in.release(); c->d_out.release(); c->d_scratch.release(); c->d_ctr.release();
     if (c->h_out) cudaFreeHost(c->h_out);
     if (c->h_in) cudaFreeHost(c->h_in);
+    if (c->h_ctr) cudaFreeHost(c->h_ctr);
     for (int b = 0; b <= kNumBuckets; b++) { if (c->bstream[b]) cudaStreamDestroy(c->bstream[b]); if (c->bev[b]) cudaEventDestroy(c->bev[b]); if (c->bev0[b]) cudaEventDestroy(c->bev0[b]); }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1361,7 +1366,7 @@ extern "C" fb_status fb_get_counters(const fb_ctx* c, FbCounters* out) {
     if (c->bucketStats) {
         fprintf(stderr, "bucket stats dev %d (cumulative; buckets overlap on the device): total %.0f ms |", c->device, c->ctr.device_ms);
         for (int b = 0; b <= kNumBuckets; b++) fprintf(stderr, " b%d%s: %.0f ms %lld items %lld launches |", b, b == kNumBuckets ? "(global tables)" : "", c->bucketMs[b], c->bucketItems[b], c->bucketLaunches[b]);
-        fprintf(stderr, "\n");
+        fprintf(stderr, " fb_em_run host: prep %.3f s, wait %.3f s, post %.3f s, %lld items\n", c->hostPrepS, c->hostWaitS, c->hostPostS, c->hostItems);
     }
     if (c->device < 64) { DevClock& k = g_clock[c->device]; std::lock_guard<std::mutex> l(k.mu); out->device_union_ms = k.unionMs; }
     return FB_OK;
@@ -1372,6 +1377,7 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
     if (!c->haveModel || !c->haveBatch) { c->err = "model/batch not uploaded"; return FB_ERR_STATE; }
     if (n == 0) return FB_OK;
     CK(cudaSetDevice(c->device));
+    const auto tRun0 = std::chrono::steady_clock::now();
     auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
     std::vector<DevItem> di(n);
     size_t outTotal = 0, inTotal = 0, scratchTotal = 0, metaTotal = 0;
@@ -1438,13 +1444,15 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
         int fill[kNumBuckets + 1];
         for (int b = 0; b <= kNumBuckets; b++) fill[b] = bucketBegin[b];
         for (int i = 0; i < n; i++) order[fill[bucketOf[i]]++] = i;
-        auto cost = [&](int i) {
+        // (keys computed once per item, not once per comparison)
+        std::vector<float> key(n);
+        for (int i = 0; i < n; i++) {
             const DevGap& g = c->hGaps[items[i].gap];
-            const double rounds = items[i].kind == FB_ITEM_HARD ? 0.3 : (g.mode == FB_MODE_UNMAPPED ? 12.0 : 3.0);
-            return rounds * (double)g.n_reads * (double)(items[i].cand_len + 100);
-        };
+            const float rounds = items[i].kind == FB_ITEM_HARD ? 0.3f : (g.mode == FB_MODE_UNMAPPED ? 12.0f : 3.0f);
+            key[i] = rounds * (float)g.n_reads * (float)(items[i].cand_len + 100);
+        }
         for (int b = 0; b <= kNumBuckets; b++)
-            std::stable_sort(order.begin() + bucketBegin[b], order.begin() + bucketBegin[b + 1], [&](int x, int y) { return cost(x) > cost(y); });
+            std::stable_sort(order.begin() + bucketBegin[b], order.begin() + bucketBegin[b + 1], [&](int x, int y) { return key[x] > key[y]; });
     }
     // ---- stage inputs
     const size_t itemsBytes = al(sizeof(DevItem) * (size_t)n);
@@ -1498,10 +1506,12 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
     }
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaMemcpyAsync(c->h_out, c->d_out.p, outTotal, cudaMemcpyDeviceToHost, c->stream));
-    unsigned long long hc[32] = {0};
-    CK(cudaMemcpyAsync(hc, c->d_ctr.p, sizeof hc, cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long* const hc = c->h_ctr;
+    CK(cudaMemcpyAsync(hc, c->d_ctr.p, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaEventRecord(c->evDone, c->stream));
+    const auto tRun1 = std::chrono::steady_clock::now();
     CK(cudaEventSynchronize(c->evDone));
+    const auto tRun2 = std::chrono::steady_clock::now();
     float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     if (c->bucketStats) for (int b = 0; b <= kNumBuckets; b++) if (bucketCount[b]) {
         float bm = 0; if (cudaEventElapsedTime(&bm, c->bev0[b], c->bev[b]) == cudaSuccess) c->bucketMs[b] += bm;
@@ -1535,6 +1545,11 @@ extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items, int32_t n, co
         H->off_p1max = di[i].off_p1; H->off_p2max = di[i].off_p2; H->off_pos2 = di[i].off_pos; H->off_soft = di[i].off_soft;
         H->off_hard = di[i].off_hard; H->off_cov = di[i].off_cov; H->off_counts = di[i].off_counts;
         out[i] = H;
+    }
+    if (c->bucketStats) {
+        const auto tRun3 = std::chrono::steady_clock::now();
+        c->hostPrepS += std::chrono::duration<double>(tRun1 - tRun0).count(); c->hostWaitS += std::chrono::duration<double>(tRun2 - tRun1).count();
+        c->hostPostS += std::chrono::duration<double>(tRun3 - tRun2).count(); c->hostItems += n;
     }
     return FB_OK;
 }
