@@ -85,6 +85,12 @@ public:
     }
     int64_t ticks() const { return ticks_; }
     double engineSeconds() const { return tEngine_; }
+    void dumpTickLog(int lane) const {      // FIGBIRD_TICK_LOG: start (s since the lane's first tick), engine call (ms), items, gaps of every tick
+        if (!tickLog_) return;
+        std::string o = "ticklog lane " + std::to_string(lane) + " ticks " + std::to_string(log_.size()) + ":";
+        for (size_t i = 0; i < log_.size(); i++) { if (log_.size() > 60 && i >= 25 && i + 35 < log_.size()) { if (i == 25) o += " ..."; continue; } char b[96]; snprintf(b, sizeof b, " [%.3f %.1fms %d/%d]", log_[i].t, 1e3 * log_[i].d, log_[i].items, log_[i].gaps); o += b; }
+        fprintf(stderr, "%s\n", o.c_str());
+    }
 
 private:
     void flush(std::unique_lock<std::mutex>&) {
@@ -100,7 +106,9 @@ private:
         outs_.assign(wi.size(), nullptr);
         auto c0 = std::chrono::steady_clock::now();
         fb_status st = (wi.empty() || failed_) ? FB_OK : fb_em_run(ctx_, wi.data(), (int32_t)wi.size(), outs_.data());
-        tEngine_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - c0).count();
+        auto c1 = std::chrono::steady_clock::now();
+        tEngine_ += std::chrono::duration<double>(c1 - c0).count();
+        if (tickLog_) { if (ticks_ == 0) t0_ = c0; log_.push_back({std::chrono::duration<double>(c0 - t0_).count(), std::chrono::duration<double>(c1 - c0).count(), (int)wi.size(), (int)batch.size()}); }
         ticks_++;
         if (st != FB_OK) { failed_ = true; err_ = std::string("fb_em_run failed: ") + fb_last_error(ctx_); }
         size_t k = 0;
@@ -122,6 +130,10 @@ private:
     bool failed_ = false; std::string err_;
     int64_t ticks_ = 0;
     double tEngine_ = 0;
+    struct TickRec { double t, d; int items, gaps; };
+    const bool tickLog_ = getenv("FIGBIRD_TICK_LOG") != nullptr;
+    std::chrono::steady_clock::time_point t0_;
+    std::vector<TickRec> log_;
 };
 
 static void fiberEntry(unsigned lo, unsigned hi) {
@@ -227,17 +239,21 @@ static fb_ctx* acquireCtx(int device, int lane, std::string& err) {
 }
 static void releaseCtx(int device, int lane, fb_ctx* ctx) { CtxPool& P = ctxPool(); std::lock_guard<std::mutex> l(P.mu); P.idle.emplace_back((long)device * 1024 + lane, ctx); }
 
-static std::vector<int> visibleDevices() {
+// Lanes: independent (context, batch queue, worker threads, fibers) groups on one GPU.  Two throughput lanes per GPU alternate --
+// the host replay of one overlaps the kernels of the other.  A third, *latency* lane per GPU takes the gaps whose control is a long
+// chain of single-round requests (unmapped mode, N-run > 400: up to 200 host-driven rounds with border updates, Figbird.cpp:4029-4376):
+// its ticks are tiny and run beside the big batches instead of queueing one round behind each of them.
+struct LaneSpec { int device; int kind; };      // kind 0: throughput, 1: latency
+static std::vector<LaneSpec> visibleLanes() {
     std::vector<int> d;
     const char* e = getenv("FIGBIRD_GPUS");
     if (e && *e) { for (const char* p = e; *p;) { d.push_back(atoi(p)); while (*p && *p != ',') p++; if (*p) p++; } }
     if (d.empty()) d.push_back(0);
-    // lanes: independent (context, batch queue, gap threads) groups on one GPU, so that the host replay of one group
-    // overlaps the kernels of the other
     int lanes = 2;
     if (const char* l = getenv("FIGBIRD_LANES")) lanes = std::max(1, atoi(l));
-    std::vector<int> out;
-    for (int x : d) for (int i = 0; i < lanes; i++) out.push_back(x);
+    const bool latency = !(getenv("FIGBIRD_LATENCY_LANE") && atoi(getenv("FIGBIRD_LATENCY_LANE")) == 0);
+    std::vector<LaneSpec> out;
+    for (int x : d) { for (int i = 0; i < lanes; i++) out.push_back(LaneSpec{x, 0}); if (latency) out.push_back(LaneSpec{x, 1}); }
     return out;
 }
 
@@ -305,15 +321,29 @@ int fillgapsMain(int argc, const char* const* argv) {
     auto t3 = clk::now();
 
     // ---- shard gaps over GPUs: longest-processing-time-first on the cost estimate
-    std::vector<int> devs = visibleDevices();
+    const std::vector<LaneSpec> laneSpecs = visibleLanes();
+    std::vector<int> devs; for (auto& l : laneSpecs) devs.push_back(l.device);      // device of every lane
     const int nD = (int)devs.size();
-    int nGpus = 0; { std::vector<int> u(devs); std::sort(u.begin(), u.end()); nGpus = (int)(std::unique(u.begin(), u.end()) - u.begin()); }
+    std::vector<int> gpuList; for (int x : devs) if (std::find(gpuList.begin(), gpuList.end(), x) == gpuList.end()) gpuList.push_back(x);
+    const int nGpus = (int)gpuList.size();
     std::vector<std::vector<int>> shard(nD);
     {
+        // two levels, both longest-processing-time-first on the cost estimate: gaps -> GPUs, then a GPU's gaps -> its lanes
         std::vector<int> order(nG); for (int i = 0; i < nG; i++) order[i] = i;
         std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return fills[x]->prepared().cost > fills[y]->prepared().cost; });
-        std::vector<double> load(nD, 0);
-        for (int g : order) { int d = (int)(std::min_element(load.begin(), load.end()) - load.begin()); shard[d].push_back(g); load[d] += fills[g]->prepared().cost + 1; }
+        std::vector<double> gload(nGpus, 0);
+        std::vector<std::vector<int>> gshard(nGpus);
+        for (int g : order) { int d = (int)(std::min_element(gload.begin(), gload.end()) - gload.begin()); gshard[d].push_back(g); gload[d] += fills[g]->prepared().cost + 1; }
+        for (int gi = 0; gi < nGpus; gi++) {
+            std::vector<int> thr, lat;
+            for (int d = 0; d < nD; d++) if (devs[d] == gpuList[gi]) (laneSpecs[d].kind == 1 ? lat : thr).push_back(d);
+            std::vector<double> load(thr.size(), 0);
+            for (int g : gshard[gi]) {
+                if (!lat.empty() && fills[g]->prepared().sequential) { shard[lat[0]].push_back(g); continue; }
+                int k = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+                shard[thr[k]].push_back(g); load[k] += fills[g]->prepared().cost + 1;
+            }
+        }
     }
     std::vector<GapResult> results(nG);
     std::vector<char> onlyGap(nG, 1);
@@ -375,6 +405,7 @@ int fillgapsMain(int argc, const char* const* argv) {
         // worker threads of this lane: the lanes of one GPU alternate (one waits for its kernels while the other replays), so
         // every lane may use the host threads of its GPU
         int nWorkers = std::max(1, hostThreads / std::max(1, nGpus));
+        if (laneSpecs[d].kind == 1) nWorkers = std::max(1, nWorkers / 4);
         if (const char* e = getenv("FIGBIRD_LANE_WORKERS")) nWorkers = std::max(1, atoi(e));
         nWorkers = std::max(1, std::min(nWorkers, (int)mine.size()));
         const int cap = std::max(1, (std::min((int)mine.size(), inflight) + nWorkers - 1) / nWorkers);
@@ -397,7 +428,7 @@ int fillgapsMain(int argc, const char* const* argv) {
             c1.device_union_ms -= ctr0.device_union_ms;
             devCtr[d] = c1;
         }
-        devTicks[d] = q.ticks(); devEng[d] = q.engineSeconds();
+        devTicks[d] = q.ticks(); devEng[d] = q.engineSeconds(); q.dumpTickLog(d);
         releaseCtx(devs[d], laneOf, ctx);
     });
     for (auto& t : devThreads) t.join();

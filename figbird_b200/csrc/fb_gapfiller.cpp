@@ -215,6 +215,7 @@ void GapFill::prepare() {
         double nr = (double)prep_.readLen.size();
         double offs = prep_.mode == FB_MODE_PARTIAL ? maxLen : (maxLen + 0.5 * (gapMin + gapMax));
         prep_.cost = cand * rounds * nr * offs * maxLen;
+        prep_.sequential = prep_.attempt && prep_.mode == FB_MODE_UNMAPPED && largeGapFlag_ == 1;
     }
 }
 

@@ -49,6 +49,7 @@ struct PreparedGap {
     std::vector<int32_t> pileL, pileR;  // [t][4]
     int pileLen = 0;
     double cost = 0;                    // sharding cost estimate (placements)
+    bool sequential = false;            // the gap is a long chain of single-round device requests (unmapped mode, N-run > 400)
 };
 
 class GapFill {

@@ -607,6 +607,17 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err, 
         // same histogram, pairs evaluated on threads (each pair's probabilities depend only on its two lines), then the
         // sequential read-name grouping of Figbird.cpp:1290-1349 over the stored results
         struct PairRes { const char* q1; const char* q2; int n1, n2; long double e2, prob; bool ok; };
+        // getEffectiveLength (Figbird.cpp:923-950) for every insert size of the histogram, once: sum over scaffolds at least that long
+        std::vector<long> effTab((size_t)MI + 1);
+        {
+            std::vector<long> lens; for (auto& q : sc.seq) lens.push_back((long)q.size());
+            std::sort(lens.begin(), lens.end());
+            size_t first = 0; long sumLen = 0; for (long v : lens) sumLen += v;      // scaffolds [first, end) have length >= t
+            for (long t = 0; t <= MI; t++) {
+                while (first < lens.size() && lens[first] < t) { sumLen -= lens[first]; first++; }
+                effTab[(size_t)t] = sumLen - (long)(lens.size() - first) * (t - 1);
+            }
+        }
         std::vector<std::pair<size_t, size_t>> pairs;
         pairs.reserve(lines.size() / 2 + 1);
         for (size_t li = 0; li < lines.size();) {
@@ -636,6 +647,7 @@ bool learnModel(const Args& a, const Scaffolds& sc, Model& m, std::string& err, 
                 r.e2 = x2.e;
                 long eff;
                 if (insertSize < 0) eff = totalContigLength;
+                else if (insertSize < (int)effTab.size()) eff = effTab[insertSize];
                 else { eff = 0; for (auto& q : sc.seq) if ((long)q.size() >= insertSize) eff += ((long)q.size() - insertSize + 1); }
                 r.prob = (1 / (long double)(eff)) * insertSizeProb * e1 * r.e2;
             }
