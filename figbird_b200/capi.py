@@ -55,7 +55,7 @@ class FbCounters(C.Structure):
                 ("lane_steps_p1", C.c_int64), ("lane_steps_p2", C.c_int64), ("device_union_ms", C.c_double)]
 
 
-EXPORTS = ["fb_ctx_create", "fb_ctx_destroy", "fb_last_error", "fb_engine_name", "fb_model_upload", "fb_batch_upload", "fb_em_run",
+EXPORTS = ["fb_ctx_create", "fb_ctx_destroy", "fb_ctx_set_latency_critical", "fb_last_error", "fb_engine_name", "fb_model_upload", "fb_batch_upload", "fb_em_run",
            "fb_get_counters", "fb_microbench_fp64", "fb_fillgaps_main"]
 
 
@@ -67,6 +67,7 @@ def load(lib_path=None):
     lib = C.CDLL(path)
     lib.fb_ctx_create.argtypes = [C.c_int32, C.POINTER(C.c_void_p)]; lib.fb_ctx_create.restype = C.c_int32
     lib.fb_ctx_destroy.argtypes = [C.c_void_p]; lib.fb_ctx_destroy.restype = None
+    lib.fb_ctx_set_latency_critical.argtypes = [C.c_void_p, C.c_int32]; lib.fb_ctx_set_latency_critical.restype = C.c_int32
     lib.fb_last_error.argtypes = [C.c_void_p]; lib.fb_last_error.restype = C.c_char_p
     lib.fb_engine_name.argtypes = []; lib.fb_engine_name.restype = C.c_char_p
     lib.fb_model_upload.argtypes = [C.c_void_p, C.POINTER(FbModel)]; lib.fb_model_upload.restype = C.c_int32

@@ -1139,7 +1139,7 @@ struct fb_ctx {
     bool bucketStats = false;
     double hostPrepS = 0, hostWaitS = 0, hostPostS = 0; long long hostItems = 0;      // diagnostics: wall seconds of fb_em_run's host phases
     int smemOptin = 0;
-    bool haveModel = false, haveBatch = false;
+    bool haveModel = false, haveBatch = false, latencyCritical = false;
     DevModel dm{};
     DevBuf<double> d_e, d_match, d_pdf, d_lfrf;
     std::vector<DevGap> hGaps; std::vector<int> hGapMaxLen;
@@ -1214,6 +1214,23 @@ extern "C" void fb_ctx_destroy(fb_ctx* c) {
     if (c->evDone) cudaEventDestroy(c->evDone);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
+}
+
+extern "C" fb_status fb_ctx_set_latency_critical(fb_ctx* c, int32_t on) {
+    if (!c) return FB_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    int lo = 0, hi = 0; CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // (numerically lower = higher priority)
+    const int prio = on ? hi : lo;
+    if (c->latencyCritical == (on != 0)) return FB_OK;
+    CK(cudaStreamSynchronize(c->stream));
+    for (int b = 0; b <= kNumBuckets; b++) {
+        if (c->bstream[b]) { CK(cudaStreamSynchronize(c->bstream[b])); CK(cudaStreamDestroy(c->bstream[b])); c->bstream[b] = nullptr; }
+        CK(cudaStreamCreateWithPriority(&c->bstream[b], cudaStreamNonBlocking, prio));
+    }
+    CK(cudaStreamDestroy(c->stream)); c->stream = nullptr;
+    CK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio));
+    c->latencyCritical = (on != 0);
+    return FB_OK;
 }
 
 template <class T> static fb_status upload(fb_ctx* c, DevBuf<T>& b, const T* src, size_t n) {

@@ -85,6 +85,7 @@ public:
     }
     int64_t ticks() const { return ticks_; }
     double engineSeconds() const { return tEngine_; }
+    int activeGaps() const override { return lastGaps_.load(std::memory_order_relaxed); }
     void dumpTickLog(int lane) const {      // FIGBIRD_TICK_LOG: start (s since the lane's first tick), engine call (ms), items, gaps of every tick
         if (!tickLog_) return;
         std::string o = "ticklog lane " + std::to_string(lane) + " ticks " + std::to_string(log_.size()) + ":";
@@ -96,6 +97,7 @@ private:
     void flush(std::unique_lock<std::mutex>&) {
         std::vector<Fiber*> batch; batch.swap(reqs_);
         arrived_ = 0;
+        lastGaps_.store((int)batch.size(), std::memory_order_relaxed);
         std::vector<FbWorkItem> wi;
         for (Fiber* f : batch) for (const ItemSpec& s : *f->reqItems) {
             FbWorkItem w{}; w.kind = s.kind; w.gap = f->bidx; w.cand_len = s.candLen; w.max_rounds = s.maxRounds; w.flags = s.flags;
@@ -130,6 +132,7 @@ private:
     bool failed_ = false; std::string err_;
     int64_t ticks_ = 0;
     double tEngine_ = 0;
+    std::atomic<int> lastGaps_{1 << 30};
     struct TickRec { double t, d; int items, gaps; };
     const bool tickLog_ = getenv("FIGBIRD_TICK_LOG") != nullptr;
     std::chrono::steady_clock::time_point t0_;
@@ -363,6 +366,7 @@ int fillgapsMain(int argc, const char* const* argv) {
         int laneOf = 0; for (int e2 = 0; e2 < d; e2++) if (devs[e2] == devs[d]) laneOf++;
         fb_ctx* ctx = acquireCtx(devs[d], laneOf, devErr[d]);
         if (!ctx) return;
+        fb_ctx_set_latency_critical(ctx, laneSpecs[d].kind == 1 ? 1 : 0);
         FbCounters ctr0{}; fb_get_counters(ctx, &ctr0);
         // batch of this shard
         std::vector<FbGap> fg; std::vector<int32_t> rlen, rmate, pileL, pileR; std::vector<int64_t> roff; std::vector<uint8_t> rfl, rjlo, rjcut, codes, flank;

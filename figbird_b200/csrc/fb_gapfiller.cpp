@@ -1146,8 +1146,11 @@ GapResult GapFill::run(DeviceQueue& dev, int batchGapIndex) {
     // candidates per device request: more means fewer engine calls (ticks) but more work past an early exit
     static const int chunkP = [] { const char* e = getenv("FIGBIRD_CHUNK_PARTIAL"); return e ? std::max(1, atoi(e)) : 16; }();
     static const int chunkU = [] { const char* e = getenv("FIGBIRD_CHUNK_UNMAPPED"); return e ? std::max(1, atoi(e)) : 24; }();
-    const int chunk = largeGapFlag_ ? 1 : (partialFlag ? chunkP : chunkU);
-    std::vector<ItemResult> chunkRes; int chunkBase = 0;
+    const int chunkBase = largeGapFlag_ ? 1 : (partialFlag ? chunkP : chunkU);
+    // tail of a run: once the lane's batch is down to a few gaps, a tick no longer fills the device and the remaining ticks are pure
+    // latency, so the candidates still to scan are requested further ahead (more speculation where it costs nothing)
+    static const int tailItems = [] { const char* e = getenv("FIGBIRD_TAIL_ITEMS"); return e ? std::max(0, atoi(e)) : 8192; }();
+    std::vector<ItemResult> chunkRes; int chunkFirst = 0;
     bool broke = false;
     for (; j < range; j++) {
         umaxFlags_ = 0;
@@ -1156,8 +1159,10 @@ GapResult GapFill::run(DeviceQueue& dev, int batchGapIndex) {
         if (unmapped && largeGapFlag_) {
             likelihood = largeGapRounds(gapEstimate, finalizeFlag, largeGapFlag_, false);
         } else {
-            if (j >= chunkBase + (int)chunkRes.size()) {
-                chunkBase = j;
+            if (j >= chunkFirst + (int)chunkRes.size()) {
+                chunkFirst = j;
+                int chunk = chunkBase;
+                { const int active = std::max(1, dev_->activeGaps()); if ((long)active * chunkBase < tailItems) chunk = std::min(192, std::max(chunkBase, tailItems / active)); }
                 std::vector<ItemSpec> specs;
                 for (int c = 0; c < chunk && j + c < range; c++) {
                     ItemSpec s = emSpec(gapEstimate + c);
@@ -1169,7 +1174,7 @@ GapResult GapFill::run(DeviceQueue& dev, int batchGapIndex) {
                 }
                 dev_->submit(bidx_, specs, chunkRes);
             }
-            const ItemResult& r = chunkRes[j - chunkBase];
+            const ItemResult& r = chunkRes[j - chunkFirst];
             if (unmapped && !finalizeFlag) {
                 // EM rounds ran with finalize_flag=0; the extra pass is the call with finalize_flag=1 (Figbird.cpp:6348-6352)
                 validCount_ = 0; refPlacements_ += r.placements;

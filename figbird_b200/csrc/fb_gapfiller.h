@@ -25,6 +25,9 @@ class DeviceQueue {
 public:
     virtual ~DeviceQueue() {}
     virtual void submit(int batchGapIndex, const std::vector<ItemSpec>& items, std::vector<ItemResult>& results) = 0;
+    // gaps that took part in the queue's most recent engine call (a large number before the first one): lets a gap speculate
+    // further ahead when the batch has become too small to fill the device (the tail of a run)
+    virtual int activeGaps() const { return 1 << 30; }
 };
 
 // Inputs of one gap as read from disk.

@@ -173,6 +173,11 @@ void fb_ctx_destroy(fb_ctx* ctx);
 const char* fb_last_error(const fb_ctx* ctx);
 const char* fb_engine_name(void);  /* "cuda-sm100a" for the product library */
 
+/* Scheduling hint: a context whose requests are small and sequentially dependent (one EM round per call, the host decides
+ * between rounds: the large-gap loop of Figbird.cpp:6323-6344 with the border update :4029-4376) asks for its kernels to be
+ * scheduled ahead of the bulk launches of other contexts on the same GPU (CUDA stream priority).  Results are unaffected. */
+fb_status fb_ctx_set_latency_critical(fb_ctx* ctx, int32_t on);
+
 fb_status fb_model_upload(fb_ctx* ctx, const FbModel* model);
 fb_status fb_batch_upload(fb_ctx* ctx, const FbGapBatch* batch);
 

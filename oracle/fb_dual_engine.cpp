@@ -25,12 +25,13 @@ struct Api {
     fb_status (*em_run)(fb_ctx*, const FbWorkItem*, int32_t, const FbItemOut**);
     fb_status (*get_counters)(const fb_ctx*, FbCounters*);
     fb_status (*microbench)(fb_ctx*, double*);
+    fb_status (*set_latency)(fb_ctx*, int32_t);
     bool load(const char* path) {
         h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
         if (!h) { fprintf(stderr, "fb_dual: dlopen %s: %s\n", path, dlerror()); return false; }
 #define SYM(f, n) *(void**)(&f) = dlsym(h, n); if (!f) { fprintf(stderr, "fb_dual: %s lacks %s\n", path, n); return false; }
         SYM(ctx_create, "fb_ctx_create") SYM(ctx_destroy, "fb_ctx_destroy") SYM(last_error, "fb_last_error") SYM(model_upload, "fb_model_upload")
-        SYM(batch_upload, "fb_batch_upload") SYM(em_run, "fb_em_run") SYM(get_counters, "fb_get_counters") SYM(microbench, "fb_microbench_fp64")
+        SYM(batch_upload, "fb_batch_upload") SYM(em_run, "fb_em_run") SYM(get_counters, "fb_get_counters") SYM(microbench, "fb_microbench_fp64") SYM(set_latency, "fb_ctx_set_latency_critical")
 #undef SYM
         return true;
     }
@@ -76,6 +77,7 @@ extern "C" fb_status fb_model_upload(fb_ctx* c, const FbModel* m) { c->cutoff = 
 extern "C" fb_status fb_batch_upload(fb_ctx* c, const FbGapBatch* b) { fb_status s = dev().batch_upload(c->d, b); return s ? s : ora().batch_upload(c->o, b); }
 extern "C" fb_status fb_get_counters(const fb_ctx* c, FbCounters* o) { return dev().get_counters(c->d, o); }
 extern "C" fb_status fb_microbench_fp64(fb_ctx* c, double* o) { return dev().microbench(c->d, o); }
+extern "C" fb_status fb_ctx_set_latency_critical(fb_ctx* c, int32_t on) { return dev().set_latency(c->d, on); }
 extern "C" int32_t fb_fillgaps_main(int32_t, const char* const*);   // provided by the host sources linked into this library
 
 extern "C" fb_status fb_em_run(fb_ctx* c, const FbWorkItem* items_in, int32_t n, const FbItemOut** out) {

@@ -190,6 +190,9 @@ def run_reference_workers_parallel(case, mode, threads, worker="figbird_worker_O
 def run_ours(case, mode, exe, threads=1, extra_env=None, name="ours"):
     run = _fresh_tmp(case, mode, name)
     env = dict(os.environ)
+    if os.path.dirname(os.path.abspath(exe)) == OBUILD:
+        # CPU engines: no extra speculation at the tail of a run (it costs nothing on a GPU, minutes on the CPU restatement)
+        env.setdefault("FIGBIRD_TAIL_ITEMS", "0")
     if extra_env:
         env.update(extra_env)
     t0 = time.time()

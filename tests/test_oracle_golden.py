@@ -109,6 +109,18 @@ def test_sharding_over_two_contexts_is_invariant(case):
         assert one[f] == two[f]
 
 
+def test_tail_speculation_is_invariant(case):
+    """Requesting candidates further ahead once a lane's batch is small (the tail of a run) changes what is evaluated
+    speculatively, never what is written."""
+    if os.path.basename(case) != "g1":
+        pytest.skip("one small fixture is enough")
+    for mode in ("partial", "unmapped"):
+        o = fc.run_ours(case, mode, fc.oracle_exe(), extra_env={"FIGBIRD_TAIL_ITEMS": "4096"}, name="tail")
+        exp = gu.expected(case, mode)
+        for f in ("gapout.txt", "filledContigs.fa", "Ncount.txt", "draw.txt"):
+            assert o[f] == exp[f], (mode, f)
+
+
 @pytest.mark.parametrize("mode", ["partial", "unmapped"])
 def test_threaded_model_learning_is_identical(case, mode):
     """learnModel cut into blocks on host threads (forced small blocks) gives the same tables and cut-offs as the
