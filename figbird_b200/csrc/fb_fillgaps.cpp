@@ -445,12 +445,33 @@ int fillgapsMain(int argc, const char* const* argv) {
         bool okGapout = true, okFilled = true;
         std::thread tg([&] { okGapout = writeGapout(a.tmpDir + "gapout.txt", gaps, results); });
         std::thread td([&] {
+            // draw.txt = the gaps' texts in gap order: sizes are known, so a few threads write disjoint ranges of the file
             const int fd = open((a.tmpDir + "draw.txt").c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
             if (fd < 0) return;
-            std::string buf; buf.reserve(8u << 20);
-            auto flushBuf = [&] { size_t off = 0; while (off < buf.size()) { ssize_t k = write(fd, buf.data() + off, buf.size() - off); if (k <= 0) break; off += (size_t)k; } buf.clear(); };
-            for (auto& r : results) { buf += r.drawText; if (buf.size() >= (4u << 20)) flushBuf(); }
-            flushBuf();
+            std::vector<size_t> off(results.size() + 1, 0);
+            for (size_t i = 0; i < results.size(); i++) off[i + 1] = off[i] + results[i].drawText.size();
+            const size_t total = off[results.size()];
+            int nt = (int)std::max<size_t>(1, std::min<size_t>(6, total >> 24));
+            if (const char* e = getenv("FIGBIRD_DRAW_THREADS")) nt = std::max(1, atoi(e));      // (tests force the threaded path on small files)
+            auto writeRange = [&](size_t lo, size_t hi) {
+                std::string buf; buf.reserve(4u << 20);
+                size_t pos = off[lo];
+                auto flushBuf = [&] { size_t o2 = 0; while (o2 < buf.size()) { ssize_t k = pwrite(fd, buf.data() + o2, buf.size() - o2, (off_t)(pos + o2)); if (k <= 0) break; o2 += (size_t)k; } pos += buf.size(); buf.clear(); };
+                for (size_t i = lo; i < hi; i++) { buf += results[i].drawText; if (buf.size() >= (2u << 20)) flushBuf(); }
+                flushBuf();
+            };
+            if (nt <= 1) writeRange(0, results.size());
+            else {
+                std::vector<std::thread> th;
+                size_t lo = 0;
+                for (int t = 0; t < nt; t++) {      // ranges of about equal bytes
+                    size_t hi = lo; const size_t want = total * (t + 1) / nt;
+                    while (hi < results.size() && off[hi] < want) hi++;
+                    if (t == nt - 1) hi = results.size();
+                    th.emplace_back(writeRange, lo, hi); lo = hi;
+                }
+                for (auto& x : th) x.join();
+            }
             close(fd);
         });
         okFilled = writeFilledContigs(a.tmpDir, sc, gaps, results, totGaps);

@@ -1147,9 +1147,11 @@ GapResult GapFill::run(DeviceQueue& dev, int batchGapIndex) {
     static const int chunkP = [] { const char* e = getenv("FIGBIRD_CHUNK_PARTIAL"); return e ? std::max(1, atoi(e)) : 16; }();
     static const int chunkU = [] { const char* e = getenv("FIGBIRD_CHUNK_UNMAPPED"); return e ? std::max(1, atoi(e)) : 24; }();
     const int chunkBase = largeGapFlag_ ? 1 : (partialFlag ? chunkP : chunkU);
-    // tail of a run: once the lane's batch is down to a few gaps, a tick no longer fills the device and the remaining ticks are pure
-    // latency, so the candidates still to scan are requested further ahead (more speculation where it costs nothing)
-    static const int tailItems = [] { const char* e = getenv("FIGBIRD_TAIL_ITEMS"); return e ? std::max(0, atoi(e)) : 8192; }();
+    // tail of a run: once the lane's batch is down to a few gaps a tick no longer fills the device, so the candidates still to scan
+    // can be requested further ahead (FIGBIRD_TAIL_ITEMS = items per tick to aim for).  Off by default: measured on C4 / 8 GPUs it
+    // saves two or three ticks but every tick still lasts as long as its slowest EM chain (~0.1 s), and the extra candidates
+    // cost 2 % more kernel time (profiles/README.md).
+    static const int tailItems = [] { const char* e = getenv("FIGBIRD_TAIL_ITEMS"); return e ? std::max(0, atoi(e)) : 0; }();
     std::vector<ItemResult> chunkRes; int chunkFirst = 0;
     bool broke = false;
     for (; j < range; j++) {

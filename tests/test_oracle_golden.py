@@ -104,7 +104,7 @@ def test_sharding_over_two_contexts_is_invariant(case):
     _light(case)
     """N>1 host path on CPU: two engine contexts (FIGBIRD_GPUS=0,1), gaps sharded cost-balanced, same files out."""
     one = fc.run_ours(case, "unmapped", fc.oracle_exe(), name="one")
-    two = fc.run_ours(case, "unmapped", fc.oracle_exe(), extra_env={"FIGBIRD_GPUS": "0,1", "FIGBIRD_INFLIGHT": "2"}, name="two")
+    two = fc.run_ours(case, "unmapped", fc.oracle_exe(), extra_env={"FIGBIRD_GPUS": "0,1", "FIGBIRD_INFLIGHT": "2", "FIGBIRD_DRAW_THREADS": "3"}, name="two")
     for f in ("gapout.txt", "filledContigs.fa", "Ncount.txt", "draw.txt"):
         assert one[f] == two[f]
 
