@@ -56,7 +56,8 @@ class FbCounters(C.Structure):
 
 
 EXPORTS = ["fb_ctx_create", "fb_ctx_destroy", "fb_ctx_set_latency_critical", "fb_last_error", "fb_engine_name", "fb_model_upload", "fb_batch_upload", "fb_em_run",
-           "fb_get_counters", "fb_microbench_fp64", "fb_fillgaps_main"]
+           "fb_get_counters", "fb_microbench_fp64", "fb_fillgaps_main",
+           "fb_preprocess_main", "fb_combinegaps_main", "fb_flanktrim_main", "fb_reduce_scf_main", "fb_reverse_main"]
 
 
 def load(lib_path=None):
@@ -206,3 +207,14 @@ def fillgaps(argv, lib_path=None):
     full = [b"fillgaps"] + [a.encode() if isinstance(a, str) else a for a in argv]
     arr = (C.c_char_p * len(full))(*full)
     return lib.fb_fillgaps_main(len(full), arr)
+
+
+def tool(name, argv, lib_path=None):
+    """The host-only pipeline tools in-process: name in preprocess / combinegaps / flanktrim / reduce_scf / reverse,
+    argv = that reference program's positional arguments (without argv[0]).  Returns its exit status."""
+    lib = load(lib_path)
+    fn = getattr(lib, "fb_%s_main" % name)
+    fn.argtypes = [C.c_int32, C.POINTER(C.c_char_p)]; fn.restype = C.c_int32
+    full = [name.encode()] + [a.encode() if isinstance(a, str) else a for a in argv]
+    arr = (C.c_char_p * len(full))(*full)
+    return fn(len(full), arr)

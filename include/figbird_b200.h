@@ -196,6 +196,27 @@ fb_status fb_microbench_fp64(fb_ctx* ctx, double* out2);
  * FIGBIRD_GPUS (default: device 0); gaps are sharded cost-balanced across them. */
 int32_t fb_fillgaps_main(int32_t argc, const char* const* argv);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Level 1, the callers and consumers on either side of FillGaps: each is the reference
+ * executable of the same name as a function -- argv[0] is ignored, argv[1..] are that program's positional
+ * arguments, the files read and written are the same, the return value is its exit status.  Host-only.
+ * ---------------------------------------------------------------------------------------------------- */
+/* Preprocess.cpp:1832-2676 (RunFigbird.sh:285,338,451,472).  argv[1..13]: contig file, maxDistance, mode
+ * (1 partial / 2 unmapped), bowtie2 SAM, myout.sam to write, gapped genome, reads_1, reads_2, Gaps dir/,
+ * Temp dir/, default_setting, genome_reduction, read_reduction.  Writes gapInfo.txt, stat.txt, stat2.txt,
+ * myout.sam and Gaps/gaps_<g>.sam or Gaps/partial_gaps_<g>.sam (and the reduced read files when asked). */
+int32_t fb_preprocess_main(int32_t argc, const char* const* argv);
+/* CombineGaps.cpp:169-313 (RunFigbird.sh:777).  argv[1..2]: number of iterations, directory/ holding
+ * gapout_<itr>.txt.  Writes combined_gapstring.txt and Individual_gaps.txt there. */
+int32_t fb_combinegaps_main(int32_t argc, const char* const* argv);
+/* FlankTrim.cpp:22-233 (RunFigbird.sh:254,433).  argv[1..4]: gapped genome, trim, read length, output FASTA. */
+int32_t fb_flanktrim_main(int32_t argc, const char* const* argv);
+/* Reduce_SCF.cpp:16-152 (RunFigbird.sh:266,320).  argv[1..2]: gapped genome, Temp dir/ (-> newgenome.fa). */
+int32_t fb_reduce_scf_main(int32_t argc, const char* const* argv);
+/* Reverse.cpp:42-120 (RunFigbird.sh:166).  argv[1..2]: the two FASTQ files of a jump library; writes
+ * <stem>_reversed<ext> beside them and prints the two new paths. */
+int32_t fb_reverse_main(int32_t argc, const char* const* argv);
+
 #ifdef __cplusplus
 }
 #endif
