@@ -46,24 +46,40 @@ WORKLOADS = {
     # round-1 operating points (SAM restricted to near-gap pairs + 300 k model pairs)
     "c2n": ({"genome": 4600000, "scaffolds": 10, "gaps": 500, "gapmin": 10, "gapmax": 500, "cov": 50, "sd": 20, "near": 700, "model-pairs": 300000}, 100, 200),
     "c4s": ({"genome": 5000000, "scaffolds": 10, "gaps": 500, "gapmin": 10, "gapmax": 2000, "cov": 40, "sd": 50, "near": 1500, "model-pairs": 300000}, 150, 500),
+    # BASELINE configs[2]: the C2 draft with two libraries, the schedule of RunFigbird.sh:552-565 -- partial mode on the 200 bp fragment
+    # library, unmapped mode on the 3500 bp jump library (maxDistance 4025).  Same seed and gap spacing => the same draft for both.
+    "c3": {"partial": ({"genome": 4600000, "scaffolds": 10, "gaps": 500, "gapmin": 10, "gapmax": 500, "cov": 50, "sd": 20, "minsep": 4175, "near": 700, "model-pairs": 300000}, 100, 200),
+           "unmapped": ({"genome": 4600000, "scaffolds": 10, "gaps": 500, "gapmin": 10, "gapmax": 500, "cov": 20, "sd": 350, "minsep": 4175}, 100, 3500)},
     "c1": ({"genome": 1000000, "scaffolds": 4, "gaps": 50, "gapmin": 10, "gapmax": 500, "cov": 30, "sd": 20, "near": 700, "model-pairs": 150000}, 100, 200),
     "tiny": ({"genome": 80000, "scaffolds": 1, "gaps": 8, "gapmin": 5, "gapmax": 300, "cov": 30, "sd": 20}, 100, 200),
 }
-SEEDS = {"c4": 104, "c2": 102, "c2n": 102, "c4s": 102, "c1": 101, "tiny": 7}
+SEEDS = {"c4": 104, "c2": 102, "c3": 103, "c2n": 102, "c4s": 102, "c1": 101, "tiny": 7}
 # bounded samples of a workload for the CPU reference: same generator parameters (gap lengths, reads, coverage, density of gaps)
 # on a shorter draft.  (gaps for the reference arm, gaps for the in-line cpu_baseline of our arm)
-SAMPLE_GAPS = {"c4": (128, 16), "c4s": (128, 16), "c2": (500, 32), "c2n": (500, 32), "c1": (50, 16), "tiny": (8, 8)}
+SAMPLE_GAPS = {"c4": (128, 16), "c4s": (128, 16), "c2": (500, 32), "c3": (64, 16), "c2n": (500, 32), "c1": (50, 16), "tiny": (8, 8)}
+
+
+def gen_of(workload):
+    """Generator options of a workload (of its partial-mode library when it has two)."""
+    w = WORKLOADS[workload]
+    return w["partial"][0] if isinstance(w, dict) else w[0]
 
 
 def sample_spec(workload, gaps):
-    gen, readlen, insert = WORKLOADS[workload]
+    if isinstance(WORKLOADS[workload], dict):
+        return {m: _sample_spec(WORKLOADS[workload][m], gaps, gen_of(workload)["gaps"]) for m in ("partial", "unmapped")}
+    return _sample_spec(WORKLOADS[workload], gaps, WORKLOADS[workload][0]["gaps"])
+
+
+def _sample_spec(spec, gaps, all_gaps):
+    gen, readlen, insert = spec
     g = dict(gen)
     per_gap = g["genome"] / g["gaps"]
     nsc = max(1, min(g["scaffolds"], gaps // 16))
     g.update({"gaps": gaps, "scaffolds": nsc, "genome": int(per_gap * gaps)})
     g.pop("threads", None)
     if "model-pairs" in g:
-        g["model-pairs"] = max(20000, int(g["model-pairs"] * gaps / WORKLOADS[workload][0]["gaps"]))
+        g["model-pairs"] = max(20000, int(g["model-pairs"] * gaps / all_gaps))
     return (g, readlen, insert)
 
 
@@ -73,7 +89,24 @@ def rank_info():
 
 
 def prepare_case(path, spec, seed):
+    """Returns the case directory; for a two-library workload a dict {mode: directory of that mode's library}."""
     import fbcase as fc
+    if isinstance(spec, dict):
+        cases = {m: prepare_case(os.path.join(path, m + "_lib"), spec[m], seed) for m in ("partial", "unmapped")}
+        a, b = (open(os.path.join(cases[m], "draft.fa"), "rb").read() for m in ("partial", "unmapped"))
+        if a != b:
+            raise RuntimeError("two-library workload: the two libraries were generated on different drafts")
+        # RunFigbird.sh keeps ONE Gaps/ directory: the unmapped pass finds the partial files the fragment library left there
+        pg, ug = os.path.join(cases["partial"], "partial", "Gaps"), os.path.join(cases["unmapped"], "unmapped", "Gaps")
+        marker = os.path.join(ug, ".partial_from_fragment_library")
+        if not os.path.exists(marker):
+            for f in os.listdir(pg):
+                dst = os.path.join(ug, f)
+                if os.path.lexists(dst):
+                    os.remove(dst)
+                os.link(os.path.join(pg, f), dst)
+            open(marker, "w").close()
+        return cases
     gen, readlen, insert = spec
     if os.path.exists(os.path.join(path, "params.txt")):
         return path
@@ -122,13 +155,14 @@ def run_step_ours(case, workdir, metrics):
     from figbird_b200 import capi
     tot = {}
     for mode in ("partial", "unmapped"):
+        mcase = case[mode] if isinstance(case, dict) else case
         tmp = os.path.join(workdir, mode, "Temp")
         os.makedirs(tmp, exist_ok=True)
         for f in ("gapInfo.txt", "stat.txt", "stat2.txt"):
-            shutil.copy(os.path.join(case, mode, "Temp", f), os.path.join(tmp, f))
+            shutil.copy(os.path.join(mcase, mode, "Temp", f), os.path.join(tmp, f))
         mpath = os.path.join(workdir, "metrics_%s.json" % mode)
         os.environ["FIGBIRD_METRICS"] = mpath
-        rc = capi.fillgaps(fc.fillgaps_argv(case, mode, tmp, threads=os.cpu_count() or 1))
+        rc = capi.fillgaps(fc.fillgaps_argv(mcase, mode, tmp, threads=os.cpu_count() or 1))
         if rc != 0:
             raise RuntimeError("fb_fillgaps_main returned %d" % rc)
         m = json.load(open(mpath))
@@ -148,24 +182,34 @@ def count_reference_placements(case, cores):
     import fbcase as fc
     total = 0
     for mode in ("partial", "unmapped"):
-        cdir = os.path.join(case, "count_" + mode)
+        mcase = case[mode] if isinstance(case, dict) else case
+        cdir = os.path.join(mcase, "count_" + mode)
         shutil.rmtree(cdir, ignore_errors=True); os.makedirs(cdir)
         os.environ["FB_COUNT_DIR"] = cdir
         try:
-            fc.run_reference_workers_parallel(case, mode, cores, "figbird_worker_count")
+            fc.run_reference_workers_parallel(mcase, mode, cores, "figbird_worker_count")
         finally:
             os.environ.pop("FB_COUNT_DIR", None)
         total += sum(int(open(os.path.join(cdir, f)).read()) for f in os.listdir(cdir))
     return total
 
 
+def mode_case(case, mode):
+    return case[mode] if isinstance(case, dict) else case
+
+
 def run_step_reference(case, threads):
     import fbcase as fc
-    return sum(fc.run_reference(case, mode, threads=threads, worker="figbird_worker_O0")["seconds"] for mode in ("partial", "unmapped"))
+    return sum(fc.run_reference(mode_case(case, mode), mode, threads=threads, worker="figbird_worker_O0")["seconds"] for mode in ("partial", "unmapped"))
+
+
+def steady_reference(case, cores, worker):
+    import fbcase as fc
+    return sum(fc.run_reference_workers_parallel(mode_case(case, mode), mode, cores, worker) for mode in ("partial", "unmapped"))
 
 
 def gaps_of(case):
-    return len(open(os.path.join(case, "partial", "Temp", "gapInfo.txt")).readlines())
+    return len(open(os.path.join(mode_case(case, "partial"), "partial", "Temp", "gapInfo.txt")).readlines())
 
 
 def main():
@@ -192,8 +236,11 @@ def main():
     base = os.environ.get("FB_BENCH_DIR", "/tmp/fb_bench")
     unit = "placements/s"
     metric = "read x offset placements scored per second (pass 1, as the reference counts them); gap-fill of synthetic %s" % a.workload
-    config = {"workload": "%s: %s, readlen %d, insert %d; step = FillGaps partial + unmapped (RunFigbird.sh:352) on one draft" % (
-                  a.workload, json.dumps({k: v for k, v in WORKLOADS[a.workload][0].items() if k != "threads"}, sort_keys=True), WORKLOADS[a.workload][1], WORKLOADS[a.workload][2]),
+    def describe(spec):
+        return "%s, readlen %d, insert %d" % (json.dumps({k: v for k, v in spec[0].items() if k != "threads"}, sort_keys=True), spec[1], spec[2])
+    w = WORKLOADS[a.workload]
+    wtext = ("partial mode on library {%s}, unmapped mode on library {%s}" % (describe(w["partial"]), describe(w["unmapped"]))) if isinstance(w, dict) else describe(w)
+    config = {"workload": "%s: %s; step = FillGaps partial + unmapped (RunFigbird.sh:352) on one draft" % (a.workload, wtext),
               "l2": "flushed between steps (256 MiB device memset per GPU); the per-step inputs are far larger than L2",
               "sharding": "ONE draft; its gaps are sharded cost-balanced over the N GPUs in-process from rank 0 (FIGBIRD_GPUS=0..N-1); strong scaling, no collective on the path"}
 
@@ -204,7 +251,7 @@ def main():
             emit({"impl": "reference", "unavailable": "oracle/_ref not built (no /root/reference at build time)"})
             return 0
         ng = SAMPLE_GAPS[a.workload][0]
-        whole = ng >= WORKLOADS[a.workload][0]["gaps"]
+        whole = ng >= gen_of(a.workload)["gaps"]
         if whole:
             sample = prepare_case(os.path.join(base, a.workload), WORKLOADS[a.workload], SEEDS[a.workload])
         else:
@@ -216,10 +263,10 @@ def main():
         t, done = 0.0, 0
         while done < max(a.steps, 1) and (done == 0 or t + t / done <= budget):
             t += run_step_reference(sample, cores); done += 1
-        steady = sum(fc.run_reference_workers_parallel(sample, mode, cores, "figbird_worker_O0") for mode in ("partial", "unmapped"))
+        steady = steady_reference(sample, cores, "figbird_worker_O0")
         v = placements * done / t
         what = ("the whole %s workload" % a.workload) if whole else (
-            "%d-gap sample of the %s workload (same generator parameters, %d bp draft)" % (ng, a.workload, sample_spec(a.workload, ng)[0]["genome"]))
+            "%d-gap sample of the %s workload (same generator parameters, %d bp draft)" % (ng, a.workload, int(gen_of(a.workload)["genome"] / gen_of(a.workload)["gaps"] * ng)))
         cfg = dict(config); cfg["workload"] = config["workload"] + " -- reference arm ran: " + what
         line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": a.gpus, "steps": done, "warmup": 1, "steps_requested": a.steps, "warmup_requested": a.warmup,
                 "ms_per_step": 1e3 * t / done, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
@@ -251,7 +298,7 @@ def main():
     work = os.path.join(base, "work_%s" % a.workload)
     t_prep0 = time.perf_counter()
     if rank == 0:
-        prepare_case(case, WORKLOADS[a.workload], SEEDS[a.workload])
+        case = prepare_case(case, WORKLOADS[a.workload], SEEDS[a.workload])
     t_prep = time.perf_counter() - t_prep0
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     metrics, warm = [], []
@@ -354,13 +401,28 @@ def main():
             "gpu_launches": int(launches), "placements": {"reference_equivalent_p1": ref_p1, "device_p1": dev_p1, "device_p2": dev_p2,
                                                           "note": "device counts include speculative candidates past the reference's early exits"},
             "value_device_placements": dev_p1 / (dev_ms * 1e-3), "data_prep_s": t_prep, "roofline": roof}
+    # at-size parity: the gapout.txt lines of the last step against the reference worker's lines for a seeded sample of the gaps
+    # (tests/golden/<workload>_sample.json, made by tools/make_sample_expect.py where the reference binaries run)
+    exp_path = os.path.join(ROOT, "tests", "golden", "%s_sample.json" % a.workload)
+    if os.path.exists(exp_path):
+        exp = json.load(open(exp_path))
+        ps = {"gaps_sampled": len(exp["gaps"]), "of": ngaps, "reference": "oracle/_ref %s on the same seeded case" % exp.get("worker", "worker")}
+        for mode in ("partial", "unmapped"):
+            ours = {}
+            for ln in open(os.path.join(work, mode, "Temp", "gapout.txt")):
+                ours[ln.split("\t", 1)[0]] = ln
+            ps["identical_" + mode] = sum(1 for g, ln in exp[mode].items() if ours.get(g) == ln)
+            bad = [int(g) for g, ln in exp[mode].items() if ours.get(g) != ln]
+            if bad:
+                ps["different_" + mode] = sorted(bad)[:20]
+        line["parity_sample"] = ps
     if world == 1 and not a.no_cpu_baseline and fc.have_reference():
         ng = SAMPLE_GAPS[a.workload][1]
         sample = prepare_case(os.path.join(base, "%s_sample%d" % (a.workload, ng)), sample_spec(a.workload, ng), SEEDS[a.workload] + 2000)
         placements = count_reference_placements(sample, cores)
         secs = run_step_reference(sample, cores)
-        steady = sum(fc.run_reference_workers_parallel(sample, mode, cores, "figbird_worker_O0") for mode in ("partial", "unmapped"))
-        tuned = sum(fc.run_reference_workers_parallel(sample, mode, cores, "figbird_worker_O2") for mode in ("partial", "unmapped"))
+        steady = steady_reference(sample, cores, "figbird_worker_O0")
+        tuned = steady_reference(sample, cores, "figbird_worker_O2")
         line["cpu_baseline"] = {"value": placements / secs, "unit": unit, "cores": cores, "kind": "reference",
                                 "sample": "%d-gap sample of the %s workload (same generator parameters), FillGaps partial+unmapped, as-shipped -O0 worker, numthreads=%d, %.1f s; placements by the reference's own counters" % (ng, a.workload, cores, secs),
                                 "steady_state": {"value": placements / steady, "seconds": steady, "note": "same sample, %d as-shipped -O0 worker processes started together (no driver sleep, no run-time compile)" % min(cores, ng)},

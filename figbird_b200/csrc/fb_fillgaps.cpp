@@ -314,13 +314,20 @@ int fillgapsMain(int argc, const char* const* argv) {
     const int ioThreads = std::max(1, std::min(a.numThreads > 0 ? a.numThreads : 1, 64));
     int hostThreads = std::max(ioThreads, (int)std::thread::hardware_concurrency());
     if (const char* e = getenv("FIGBIRD_HOST_THREADS")) hostThreads = std::max(1, atoi(e));     // several ranks on one host share its cores
+    std::atomic<long long> tIo(0), tCtor(0), tPrep(0);
     parallelFor(nG, hostThreads, [&](int g) {
+        auto x0 = clk::now();
         GapInput in; in.rec = gaps[g];
         loadPartial(a.gapsDir + "partial_gaps_" + std::to_string(g) + ".sam", in.partial, in.partialExists);
         if (a.unmapped == 1) loadUnmapped(a.gapsDir + "gaps_" + std::to_string(g) + ".sam", a.readLength, in.unm, in.unmPairCount);
+        auto x1 = clk::now();
         fills[g].reset(new GapFill(a, model, sc, std::move(in)));
+        auto x2 = clk::now();
         fills[g]->prepare();
+        auto x3 = clk::now();
+        tIo += std::chrono::duration_cast<std::chrono::nanoseconds>(x1 - x0).count(); tCtor += std::chrono::duration_cast<std::chrono::nanoseconds>(x2 - x1).count(); tPrep += std::chrono::duration_cast<std::chrono::nanoseconds>(x3 - x2).count();
     });
+    if (getenv("FIGBIRD_PREP_TIMING")) fprintf(stderr, "prepare: threads %d, summed over threads: load %.3f s, ctor %.3f s, prepare %.3f s\n", hostThreads, tIo.load() * 1e-9, tCtor.load() * 1e-9, tPrep.load() * 1e-9);
     auto t3 = clk::now();
 
     // ---- shard gaps over GPUs: longest-processing-time-first on the cost estimate

@@ -108,15 +108,8 @@ void GapFill::prepare() {
     partialPosOrg_.assign(partialReadCount_, std::array<int, 3>{{0, -200, 0}});
 
     // parsePartial: per-base error probabilities of partial reads (qualityFilter, Figbird.cpp:1780-1797, 5829-5836)
-    if (a_.partialFlag) {
-        partialQuality_.resize(partialReadCount_);
-        for (int i = 0; i < partialReadCount_; i++) {
-            std::string q = in_.partial[i].qual;
-            if ((int)q.size() > partialReadLen_) q.resize(partialReadLen_);   // token[partial_read_len]='\0'
-            partialQuality_[i].assign(std::max<size_t>(q.size(), in_.partial[i].seq.size()), 0.0);
-            for (size_t k = 0; k < q.size(); k++) { int Q = q[k] - 33; partialQuality_[i][k] = pow(10, -Q / 10.0); }
-        }
-    }
+    // -- evaluated where finalize() adds them up (partialQualityAt): a table per read would be written for every gap and read
+    //    for the few reads finalize accepts
 
     // ---- supported domain + flanks
     const std::string& ctg = sc_.seq[r.contigNo];
@@ -219,6 +212,12 @@ void GapFill::prepare() {
     }
 }
 
+// 10^(-Q/10), Q = char - 33 (qualityFilter, Figbird.cpp:1780-1797): one pow() per distinct character instead of one per base
+double GapFill::phredError(unsigned char ch) {
+    static const std::vector<double> tab = [] { std::vector<double> t(256); for (int c = 0; c < 256; c++) { const int Q = (int)(char)c - 33; t[(size_t)c] = pow(10, -Q / 10.0); } return t; }();
+    return tab[ch];
+}
+
 // findRepeat (Figbird.cpp:1799-1911)
 int GapFill::findRepeat() {
     const int np = (int)std::min<size_t>(in_.partial.size(), 3001);
@@ -229,6 +228,10 @@ int GapFill::findRepeat() {
         const std::string& s5 = in_.partial[p].seq;
         std::vector<size_t> positions;
         int lim = (int)gapLeft_.size() - n;
+        // every flank piece tried below contains the shortest one (the last suffix of the left flank, the last prefix of the right
+        // flank), so a piece can occur twice in the read only if the shortest one does: one search settles almost every read
+        auto twice = [&](const std::string& piece) { const size_t a = s5.find(piece); return a != std::string::npos && s5.find(piece, a + 1) != std::string::npos; };
+        if (lim > 0 && !twice(gapLeft_.substr(lim - 1))) lim = 0;
         for (int i = 0; i < lim; i++) {
             std::string s3 = gapLeft_.substr(i);
             size_t pos = s5.find(s3, 0);
@@ -242,6 +245,7 @@ int GapFill::findRepeat() {
         }
         positions.clear();
         lim = (int)gapRight_.size() - n;
+        if (lim > 0 && !twice(gapRight_.substr(0, gapRight_.size() - (lim - 1)))) lim = 0;
         for (int i = 0; i < lim; i++) {
             std::string s4 = gapRight_.substr(0, gapRight_.size() - i);
             size_t pos = s5.find(s4, 0);
@@ -979,7 +983,11 @@ void GapFill::finalize(int gl) {
                     if (x >= 0 && x < gl) {
                         int cd = code(p.seq[j]);
                         counts_[x][cd] += 1;
-                        if (x < (int)qualGap_.size() && j < (int)partialQuality_[q].size()) qualGap_[x][cd] += partialQuality_[q][j];
+                        if (x < (int)qualGap_.size() && a_.partialFlag) {
+                            // quality string cut at partial_read_len (token[partial_read_len] = '\0'); bases beyond it count 0
+                            const size_t ql = std::min<size_t>(p.qual.size(), (size_t)std::max(0, partialReadLen_));
+                            if ((size_t)j < std::max(ql, p.seq.size())) qualGap_[x][cd] += (size_t)j < ql ? phredError((unsigned char)p.qual[(size_t)j]) : 0.0;
+                        }
                     }
                 }
             } else discardedCount++;
@@ -1259,7 +1267,6 @@ GapResult GapFill::run(DeviceQueue& dev, int batchGapIndex) {
     out.refPlacements = refPlacements_;
     // the per-gap working set is not needed once the result is out
     std::vector<std::array<double, 5>>().swap(counts_); std::vector<std::array<double, 5>>().swap(qualGap_);
-    std::vector<std::vector<double>>().swap(partialQuality_);
     return out;
 }
 

@@ -90,7 +90,6 @@ private:
     std::vector<int> gapCoverage_;
     std::vector<std::array<double, 5>> counts_;   // countsGap gap rows (host copy, finalize / border update)
     std::vector<std::array<double, 5>> qualGap_;
-    std::vector<std::vector<double>> partialQuality_;
     // The reference keeps `char partial_left[100], partial_right[100]; int partial_saved_read_temp[2], partial_saved_read_final[2];
     // int side_limit;` side by side (Figbird.cpp:1625-1627) and update_partial_prob writes the pile-up strings without a bound
     // (:2063-2084): with reads longer than ~105 bases partial_left runs into partial_right and partial_right into the saved-read
@@ -115,6 +114,7 @@ private:
     // ---- helpers
     bool analyze();
     int findRepeat();
+    static double phredError(unsigned char ch);
     int findContigMatch() const;
     void pileUp(int Lg, bool makeStrings);
     void initializeEffects(int Lg);     // what initialize() leaves behind on the host besides the gap rows (see ovl_)

@@ -120,38 +120,79 @@ bool loadGapRecords(const std::string& tmpDir, std::vector<GapRecord>& gaps, int
     return true;
 }
 
-static std::vector<std::string> splitTabs(const std::string& line) {
-    // strtok(line, "\t") semantics: runs of tabs collapse, the newline stays in the last token
-    std::vector<std::string> t;
-    size_t p = 0;
-    while (p < line.size()) {
-        while (p < line.size() && line[p] == '\t') p++;
-        if (p >= line.size()) break;
-        size_t e = line.find('\t', p);
-        if (e == std::string::npos) e = line.size();
-        t.push_back(line.substr(p, e - p));
-        p = e;
+// ---- per-gap read files.  A file is read with one call and walked in place: records as fgets(buf, 1024) returns them (a physical
+// line of 1023 bytes or more arrives in pieces), fields as strtok(line, "\t") yields them (runs of tabs collapse, the newline
+// stays in the last field).
+namespace {
+struct FileText {
+    std::string buf;
+    bool read(const std::string& path) {
+        const int fd = open(path.c_str(), O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0) { close(fd); return false; }
+        buf.resize((size_t)st.st_size);
+        size_t off = 0;
+        while (off < buf.size()) { const ssize_t k = ::read(fd, &buf[off], buf.size() - off); if (k <= 0) break; off += (size_t)k; }
+        close(fd);
+        buf.resize(off);
+        return true;
     }
-    return t;
+};
+struct View { const char* p; size_t n; bool empty() const { return n == 0; } };
+struct Records {
+    const char* p; const char* e;
+    explicit Records(const std::string& t) : p(t.data()), e(t.data() + t.size()) {}
+    bool next(View& r) {
+        if (p >= e) return false;
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
+        const char* le = nl ? nl + 1 : e;
+        if (le - p > 1023) le = p + 1023;
+        r.p = p; r.n = (size_t)(le - p); p = le;
+        // a NUL byte ends the C string the reference works on
+        const void* z = memchr(r.p, 0, r.n); if (z) r.n = (size_t)((const char*)z - r.p);
+        return true;
+    }
+};
+// up to `want` tab-separated fields of a record; returns how many there are in total (counting stops at 16)
+int fields(const View& r, View* out, int want) {
+    int n = 0; size_t q = 0;
+    while (q < r.n && n < 16) {
+        while (q < r.n && r.p[q] == '\t') q++;
+        if (q >= r.n) break;
+        size_t e = q; while (e < r.n && r.p[e] != '\t') e++;
+        if (n < want) out[n] = View{r.p + q, e - q};
+        n++; q = e;
+    }
+    return n;
 }
+int atoiView(const View& v) {
+    size_t i = 0; while (i < v.n && (v.p[i] == ' ' || (v.p[i] >= '\t' && v.p[i] <= '\r'))) i++;
+    bool neg = false; if (i < v.n && (v.p[i] == '+' || v.p[i] == '-')) { neg = v.p[i] == '-'; i++; }
+    long x = 0; for (; i < v.n && v.p[i] >= '0' && v.p[i] <= '9'; i++) x = x * 10 + (v.p[i] - '0');
+    return (int)(neg ? -x : x);
+}
+}  // namespace
 
 // partial_gaps_<g>.sam: seq, clipped_index, match, pos, cigar, pos2, qual (Preprocess.cpp:454,466,478).
 // Every reader in the reference stops after partial_limit+1 = 3001 lines (e.g. Figbird.cpp:1814,2014).
 bool loadPartial(const std::string& path, std::vector<PartialRead>& out, bool& exists) {
-    std::vector<std::string> lines;
-    exists = readLines(path, lines);
+    FileText ft;
+    exists = ft.read(path);
     if (!exists) return false;
-    for (auto& ln : lines) {
-        auto t = splitTabs(ln);
-        PartialRead r;
-        if (t.size() >= 1) r.seq = t[0];
-        if (t.size() >= 2) r.clippedIndex = atoi(t[1].c_str());
-        if (t.size() >= 3) r.match = atoi(t[2].c_str());
-        if (t.size() >= 4) r.pos = atoi(t[3].c_str());
-        if (t.size() >= 6) r.refPos = atoi(t[5].c_str());
-        if (t.size() >= 7) { r.qual = t[6]; while (!r.qual.empty() && (r.qual.back() == '\n' || r.qual.back() == '\r')) r.qual.pop_back(); }
-        if (t.size() == 1) { while (!r.seq.empty() && r.seq.back() == '\n') r.seq.pop_back(); }
-        out.push_back(r);
+    Records rec(ft.buf);
+    View r, t[7];
+    while (rec.next(r)) {
+        const int n = fields(r, t, 7);
+        out.emplace_back();
+        PartialRead& pr = out.back();
+        if (n >= 1) pr.seq.assign(t[0].p, t[0].n);
+        if (n >= 2) pr.clippedIndex = atoiView(t[1]);
+        if (n >= 3) pr.match = atoiView(t[2]);
+        if (n >= 4) pr.pos = atoiView(t[3]);
+        if (n >= 6) pr.refPos = atoiView(t[5]);
+        if (n >= 7) { pr.qual.assign(t[6].p, t[6].n); while (!pr.qual.empty() && (pr.qual.back() == '\n' || pr.qual.back() == '\r')) pr.qual.pop_back(); }
+        if (n == 1) { while (!pr.seq.empty() && pr.seq.back() == '\n') pr.seq.pop_back(); }
         if (out.size() > 3000) break;
     }
     return true;
@@ -165,31 +206,28 @@ static char rc(char ch) {   // reverse(), Figbird.cpp:1427-1449
 // gaps_<g>.sam (parseUnmapped, Figbird.cpp:5661-5767): line pairs, mapped mate then unmapped mate.
 // pairCount = findcount_file(.,0) (Figbird.cpp:6686-6711).
 bool loadUnmapped(const std::string& path, int readLen, std::vector<UnmappedRead>& out, int& pairCount) {
-    std::vector<std::string> lines;
+    (void)readLen;
+    FileText ft;
     pairCount = 0;
-    if (!readLines(path, lines)) return false;
-    { size_t i = 0; while (i < lines.size()) { i++; if (i >= lines.size()) break; i++; pairCount++; } }
-    size_t i = 0; int total = 0;
-    while (i < lines.size()) {
-        const std::string& l1 = lines[i++];
-        if (l1[0] == '@') continue;
-        if (l1.size() < 60) continue;
-        if (i >= lines.size()) break;
-        const std::string& l2 = lines[i++];
-        auto t1 = splitTabs(l1), t2 = splitTabs(l2);
-        if (t1.size() < 4 || t2.size() < 8) continue;
-        UnmappedRead r;
-        int flag = atoi(t1[1].c_str());
-        int strand1 = (flag & 16) >> 4;
-        r.matePos = atoi(t1[3].c_str());
-        r.seq = t2[6];
-        (void)readLen;
+    if (!ft.read(path)) return false;
+    { Records all(ft.buf); View r; size_t n = 0; while (all.next(r)) n++; pairCount = (int)(n / 2); }
+    Records rec(ft.buf);
+    View l1, l2, t1[4], t2[8];
+    int total = 0;
+    while (rec.next(l1)) {
+        if (l1.n > 0 && l1.p[0] == '@') continue;
+        if (l1.n < 60) continue;
+        if (!rec.next(l2)) break;
+        if (fields(l1, t1, 4) < 4 || fields(l2, t2, 8) < 8) continue;
+        out.emplace_back();
+        UnmappedRead& u = out.back();
+        const int strand1 = (atoiView(t1[1]) & 16) >> 4;
+        u.matePos = atoiView(t1[3]);
         if (strand1 == 0) {
-            std::string rev(r.seq.size(), 'N');
-            for (size_t k = 0; k < r.seq.size(); k++) rev[r.seq.size() - 1 - k] = rc(r.seq[k]);
-            r.seq = rev; r.isReverse = 1;
-        } else r.isReverse = 0;
-        out.push_back(r);
+            u.seq.resize(t2[6].n);
+            for (size_t k = 0; k < t2[6].n; k++) u.seq[t2[6].n - 1 - k] = rc(t2[6].p[k]);
+            u.isReverse = 1;
+        } else { u.seq.assign(t2[6].p, t2[6].n); u.isReverse = 0; }
         if (++total == 3000) break;   // unmapped_limit
     }
     return true;
