@@ -40,6 +40,12 @@ def main():
                 data = b"\n".join(b"\t".join(l.split(b"\t")[:8]) for l in data.split(b"\n"))
             e[f] = hashlib.md5(data).hexdigest()
         exp[mode] = e
+    # what the reference FillGaps makes of those inputs: the end-to-end expectation of "our Preprocess, then our FillGaps"
+    for mode in ("partial", "unmapped"):
+        r = fc.run_reference(case, mode, threads=4)
+        exp["fillgaps_" + mode] = {f: hashlib.md5(r[f]).hexdigest() for f in ("gapout.txt", "filledContigs.fa", "Ncount.txt")}
+        exp["fillgaps_" + mode]["draw.txt (per gap, sorted)"] = hashlib.md5(repr(sorted(fc.draw_by_gap(r["draw.txt"]).items())).encode()).hexdigest()
+    exp["readlen"], exp["insert"] = READLEN, INSERT
     json.dump(exp, open(os.path.join(dst, "expected.json"), "w"), indent=1, sort_keys=True)
     out = os.path.join(HERE, "golden", "pp1.tar.gz")
     with tarfile.open(out, "w:gz") as t:

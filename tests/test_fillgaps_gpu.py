@@ -131,3 +131,34 @@ def test_c2_full_size_against_reference_golden(tmp_path_factory):
         exp = gzip.open(os.path.join(gu.GOLDEN, "c2_gapout_%s.txt.gz" % mode)).read()
         assert o["gapout.txt"] == exp, "c2 %s gapout differs from the reference" % mode
         assert hashlib.md5(o["filledContigs.fa"]).hexdigest() == md5s[i]
+
+
+def test_pipeline_our_preprocess_then_our_fillgaps(tmp_path):
+    """The two stages chained without any reference program: bowtie2-style SAM -> fb_preprocess_main -> fb_fillgaps_main, against
+    what the reference Preprocess + reference FillGaps made of the same SAM (tests/golden/pp1.tar.gz, tests/make_pp_golden.py)."""
+    import hashlib
+    import json
+    import shutil
+    import tarfile
+    from figbird_b200 import capi
+    with tarfile.open(os.path.join(gu.GOLDEN, "pp1.tar.gz")) as t:
+        t.extractall(str(tmp_path), filter="data")
+    case = str(tmp_path / "pp1")
+    exp = json.load(open(os.path.join(case, "expected.json")))
+    if "fillgaps_partial" not in exp:
+        pytest.skip("fixture without FillGaps expectations")
+    draft = os.path.join(case, "draft.fa")
+    gaps = os.path.join(case, "Gaps") + "/"        # ONE Gaps/ directory for both passes, as RunFigbird.sh keeps it
+    os.makedirs(gaps)
+    for mode, flag, sam in (("partial", "1", "result1.sam"), ("unmapped", "2", "result2.sam")):
+        d = os.path.join(case, mode); tmp = os.path.join(d, "Temp") + "/"
+        os.makedirs(tmp)
+        assert capi.tool("preprocess", [draft, str(exp["x"][mode]), flag, os.path.join(case, sam), os.path.join(d, "myout.sam"), draft, "r1.fq", "r2.fq", gaps, tmp, "1", "0", "0"]) == 0
+        pf, um = ("1", "0") if mode == "partial" else ("0", "1")
+        argv = [draft, str(exp["x"][mode]), str(exp["readlen"]), "1", pf, um, "4", os.path.join(d, "myout.sam"), tmp, gaps, "30", str(exp["readlen"]), "0", "0", str(exp["insert"])]
+        assert capi.fillgaps(argv) == 0
+        out = fc.read_outputs(tmp)
+        for f in ("gapout.txt", "filledContigs.fa", "Ncount.txt"):
+            assert hashlib.md5(out[f]).hexdigest() == exp["fillgaps_" + mode][f], "%s %s" % (mode, f)
+        assert hashlib.md5(repr(sorted(fc.draw_by_gap(out["draw.txt"]).items())).encode()).hexdigest() == exp["fillgaps_" + mode]["draw.txt (per gap, sorted)"], mode
+    shutil.rmtree(case, ignore_errors=True)
