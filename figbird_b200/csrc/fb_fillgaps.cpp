@@ -260,6 +260,53 @@ static std::vector<LaneSpec> visibleLanes() {
     return out;
 }
 
+// The order in which the reference's draw.txt lists the gaps: FillGaps deals the gaps to num_threads workers (N-runs of at most
+// 400 bases round-robin, the longer ones to the workers with the most room left; FillGaps.cpp:456-649), every worker writes its
+// gaps in ascending order (writeGapLoad :313-334, Figbird.cpp:7283-7317) and the workers' files are concatenated in worker order
+// (mergeFiles :222-258).  The sort of the workers by remaining room is std::sort with the reference's comparator on the
+// reference's container, i.e. the same unstable order for equal keys.
+static std::vector<int> referenceDrawOrder(const std::string& tmpDir, int totGaps, int numThreads) {
+    std::vector<int> order;
+    if (totGaps <= 0) return order;
+    int T = numThreads;
+    std::vector<std::vector<int>> alloc;
+    if (totGaps <= T || T < 1) {
+        for (int i = 0; i < totGaps; i++) order.push_back(i);
+        return order;
+    }
+    const float tf = (float)(totGaps * 1.0 / T);
+    int per = (int)tf;
+    if (tf - float(per) > 0) per++;
+    std::vector<int> small, large;
+    {
+        FILE* f = fopen((tmpDir + "gapInfo.txt").c_str(), "r");
+        if (!f) { for (int i = 0; i < totGaps; i++) order.push_back(i); return order; }
+        char line[1024]; int cnt = 0;
+        while (fgets(line, sizeof line, f)) {
+            char* t = strtok(line, "\t"); t = strtok(nullptr, "\t"); t = strtok(nullptr, "\t\n");
+            const int gaplen = t ? atoi(t) : 0;
+            (gaplen > 400 ? large : small).push_back(cnt);
+            cnt++;
+        }
+        fclose(f);
+    }
+    alloc.assign((size_t)T, std::vector<int>());
+    const int nSmall = (int)small.size(), nLarge = (int)large.size();
+    if (nSmall <= T) { for (int i = 0; i < nSmall; i++) alloc[(size_t)i].push_back(small[(size_t)i]); }
+    else { for (int k = 0; k < nSmall; k++) alloc[(size_t)(k % T)].push_back(small[(size_t)k]); }
+    std::vector<std::vector<int>> rem((size_t)T);
+    for (int i = 0; i < T; i++) rem[(size_t)i] = std::vector<int>{i, per - (int)alloc[(size_t)i].size()};
+    std::sort(rem.begin(), rem.end(), [](const std::vector<int>& a, const std::vector<int>& b) { return a[1] > b[1]; });
+    int k = 0;
+    if (nLarge <= T) { for (int i = 0; i < T && k < nLarge; i++) alloc[(size_t)rem[(size_t)i][0]].push_back(large[(size_t)k++]); }
+    else {
+        for (int i = 0; i < T && k < nLarge; i++)
+            for (int j = 0; j < rem[(size_t)i][1] && k < nLarge; j++) alloc[(size_t)rem[(size_t)i][0]].push_back(large[(size_t)k++]);
+    }
+    for (auto& a : alloc) { std::sort(a.begin(), a.end()); for (int g : a) order.push_back(g); }
+    return order;
+}
+
 struct RunStats { double tLoad = 0, tModel = 0, tPrep = 0, tFill = 0, tWrite = 0, tEngine = 0, tCopy = 0, tCtx = 0, tWorkers = 0, cpuWorkers = 0; int64_t refPlacements = 0; FbCounters dev{}; int64_t ticks = 0; };
 
 int fillgapsMain(int argc, const char* const* argv) {
@@ -452,11 +499,16 @@ int fillgapsMain(int argc, const char* const* argv) {
         bool okGapout = true, okFilled = true;
         std::thread tg([&] { okGapout = writeGapout(a.tmpDir + "gapout.txt", gaps, results); });
         std::thread td([&] {
-            // draw.txt = the gaps' texts in gap order: sizes are known, so a few threads write disjoint ranges of the file
+            // draw.txt = the gaps' texts in the order the reference's workers would have left them (FIGBIRD_DRAW_ORDER=gap: in gap
+            // order): sizes are known, so a few threads write disjoint ranges of the file
             const int fd = open((a.tmpDir + "draw.txt").c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
             if (fd < 0) return;
+            std::vector<int> seq;
+            { const char* e = getenv("FIGBIRD_DRAW_ORDER"); if (!(e && !strcmp(e, "gap"))) seq = referenceDrawOrder(a.tmpDir, totGaps, a.numThreads); }
+            { std::vector<int> keep; std::vector<char> seen(results.size(), 0); for (int g : seq) if (g >= 0 && (size_t)g < results.size() && !seen[(size_t)g]) { seen[(size_t)g] = 1; keep.push_back(g); }
+              for (size_t g = 0; g < results.size(); g++) if (!seen[g]) keep.push_back((int)g); seq.swap(keep); }
             std::vector<size_t> off(results.size() + 1, 0);
-            for (size_t i = 0; i < results.size(); i++) off[i + 1] = off[i] + results[i].drawText.size();
+            for (size_t i = 0; i < results.size(); i++) off[i + 1] = off[i] + results[(size_t)seq[i]].drawText.size();
             const size_t total = off[results.size()];
             int nt = (int)std::max<size_t>(1, std::min<size_t>(6, total >> 24));
             if (const char* e = getenv("FIGBIRD_DRAW_THREADS")) nt = std::max(1, atoi(e));      // (tests force the threaded path on small files)
@@ -464,7 +516,7 @@ int fillgapsMain(int argc, const char* const* argv) {
                 std::string buf; buf.reserve(4u << 20);
                 size_t pos = off[lo];
                 auto flushBuf = [&] { size_t o2 = 0; while (o2 < buf.size()) { ssize_t k = pwrite(fd, buf.data() + o2, buf.size() - o2, (off_t)(pos + o2)); if (k <= 0) break; o2 += (size_t)k; } pos += buf.size(); buf.clear(); };
-                for (size_t i = lo; i < hi; i++) { buf += results[i].drawText; if (buf.size() >= (2u << 20)) flushBuf(); }
+                for (size_t i = lo; i < hi; i++) { buf += results[(size_t)seq[i]].drawText; if (buf.size() >= (2u << 20)) flushBuf(); }
                 flushBuf();
             };
             if (nt <= 1) writeRange(0, results.size());

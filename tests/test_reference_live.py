@@ -19,3 +19,18 @@ def test_oracle_equals_reference_on_fresh_case(tmp_path, seed, gen):
         for f in ("gapout.txt", "filledContigs.fa", "Ncount.txt"):
             assert r[f] == o[f], "%s %s" % (mode, f)
         assert fc.draw_by_gap(r["draw.txt"]) == fc.draw_by_gap(o["draw.txt"])
+
+
+@pytest.mark.parametrize("threads", [1, 4, 7])
+def test_draw_txt_in_the_reference_worker_order(tmp_path, threads):
+    """draw.txt is the concatenation of the workers' files, so its order depends on num_threads and on the reference's dealing of
+    small and large gaps to the workers (FillGaps.cpp:456-649): reproduced, byte for byte (partial mode: cheap on the CPU engine)."""
+    g = {"genome": 60000, "gaplist": "12,450,45,95,20,520,30,60,25,14,33", "cov": 14, "seed": 43}
+    case = fc.make_case(str(tmp_path / "case"), g)
+    r = fc.run_reference(case, "partial", threads=threads)
+    o = fc.run_ours(case, "partial", fc.oracle_exe(), threads=threads)
+    for f in ("gapout.txt", "filledContigs.fa", "Ncount.txt", "draw.txt"):
+        assert r[f] == o[f], "%s (num_threads %d)" % (f, threads)
+    if threads > 1:
+        og = fc.run_ours(case, "partial", fc.oracle_exe(), threads=threads, extra_env={"FIGBIRD_DRAW_ORDER": "gap"}, name="gaporder")
+        assert og["draw.txt"] != r["draw.txt"] and fc.draw_by_gap(og["draw.txt"]) == fc.draw_by_gap(r["draw.txt"])
