@@ -209,7 +209,15 @@ __device__ __forceinline__ void band(const DevModel& m, const DevGap& g, int fl,
 #ifndef FB_WTR
 #define FB_WTR 0
 #endif
-__device__ __forceinline__ int wtr(int i, int np) { return FB_WTR ? (i & 3) * np + (i >> 2) : i; }
+#ifndef FB_WTR_BIG
+#define FB_WTR_BIG 0   // the same layout for the one-CTA-per-SM launch shape only (shared-memory wavefronts are its busiest unit)
+#endif
+#ifndef FB_TILEBAR
+#define FB_TILEBAR 0   // 1: the parts of one gather tile hand the count rows on through a named barrier of their own (the warps of that tile only)
+#endif
+#ifndef FB_HINT
+#define FB_HINT 0      // 1: a warp looks for the owner of its next work unit next to the owner of its previous one before it bisects
+#endif
 
 // base code i of a packed sequence (A0 C1 G2 T3, 4 = N / other)
 __device__ __forceinline__ int pkCode(const uint2* p, int i) { const uint2 w = p[i >> 4]; const int sft = i & 15; return ((w.y >> sft) & 1u) ? 4 : (int)((w.x >> (2 * sft)) & 3u); }
@@ -308,6 +316,8 @@ __global__ void __launch_bounds__(128) fb_flank_kernel(const Params prm, int nRe
 template <bool TSMEM, int NT>
 __global__ void __launch_bounds__(NT, (TSMEM && NT == FB_THREADS) ? FB_CTAS : 1) fb_em_kernel(const Params prm, const int* __restrict__ order, const int smemBytes) {
     constexpr int kThreads = NT, kWarps = NT / 32;
+    constexpr bool kWtr = FB_WTR || (FB_WTR_BIG && NT == FB_THREADS_BIG && NT != FB_THREADS);
+    auto wtr = [](int i, int np) { return kWtr ? (i & 3) * np + (i >> 2) : i; };
     const DevItem it = prm.items[order[blockIdx.x]];
     const DevGap g = prm.gaps[it.gap];
     const DevModel& m = prm.m;
@@ -513,8 +523,17 @@ __global__ void __launch_bounds__(NT, (TSMEM && NT == FB_THREADS) ? FB_CTAS : 1)
         return s_q1;
     };
     // read of the resident chunk that owns work unit `target` (largest ql with prefix[ql] <= target); U2 selects the pass-2 prefix
-    auto findRead = [&](bool U2, int target) -> int {
+    // (units are handed out in increasing order, so the owner is usually the read of the warp's previous unit or one of the next
+    //  few: `hint` = that read; RM[nqCur] holds the total, which no unit reaches)
+    auto findRead = [&](bool U2, int target, int hint) -> int {
         int lo = 0, hi = nqCur - 1;
+#if FB_HINT
+        if ((U2 ? RM[hint].u2 : RM[hint].u1) <= target) {
+            lo = hint;
+#pragma unroll 1
+            for (int s = 0; s < 3; s++) { if ((U2 ? RM[lo + 1].u2 : RM[lo + 1].u1) > target) return lo; lo++; }
+        } else hi = hint - 1;
+#endif
         while (lo < hi) { const int mid = (lo + hi + 1) >> 1; const int v = U2 ? RM[mid].u2 : RM[mid].u1; if (v <= target) lo = mid; else hi = mid - 1; }
         return lo;
     };
@@ -615,12 +634,14 @@ __global__ void __launch_bounds__(NT, (TSMEM && NT == FB_THREADS) ? FB_CTAS : 1)
                 }
             };
             const int units = RM[nq].u2;
+            int hint2 = 0;
             for (;;) {
                 int u = 0;
                 if (lane == 0) u = atomicAdd(&s_next2, 1);
                 u = __shfl_sync(0xffffffffu, u, 0);
                 if (u >= units) break;
-                const int ql = findRead(true, u);
+                const int ql = findRead(true, u, hint2);
+                hint2 = ql;
                 const RMeta r = RM[ql];
                 const int ch = u - r.u2;
                 const int len = r.packed & 0xff, jlo = (r.packed >> 8) & 0xff, jhi = (r.packed >> 16) & 0xff;
@@ -821,12 +842,14 @@ __global__ void __launch_bounds__(NT, (TSMEM && NT == FB_THREADS) ? FB_CTAS : 1)
                 };
                 // ---- gap-row products of every admissible placement: cyclic diagonal walk
                 const int units = (Lg > 0) ? RM[nq].u1 : 0;
+                int hint1 = 0;
                 for (;;) {
                     int u = 0;
                     if (lane == 0) u = atomicAdd(&s_next1, 1);
                     u = __shfl_sync(0xffffffffu, u, 0);
                     if (u >= units) break;
-                    const int ql = findRead(false, u);
+                    const int ql = findRead(false, u, hint1);
+                    hint1 = ql;
                     const RMeta r = RM[ql];
                     const int uu = u - r.u1;
                     const int len = r.packed & 0xff, jlo = (r.packed >> 8) & 0xff, jhi = (r.packed >> 16) & 0xff;
@@ -1014,7 +1037,15 @@ __global__ void __launch_bounds__(NT, (TSMEM && NT == FB_THREADS) ? FB_CTAS : 1)
                                 w[0] = ld(i0);
                             }
                         }
-                        for (int sp = 0; sp < split; sp++) {
+#if FB_TILEBAR
+                        // every tile runs its own chain part 0 -> 1 -> ...: only the warps of that tile meet (named barrier 1 + tile), so a
+                        // tile does not wait for the slowest gather warp of another tile; the CTA meets once, after the gather
+                        const bool tileBar = tiled && nTiles <= 15;
+#else
+                        const bool tileBar = false;
+#endif
+                        for (int sp = 0; sp < (tileBar ? (myIdle ? 0 : myParts) : split); sp++) {
+                            if (tileBar && sp > 0) asm volatile("bar.sync %0, %1;" :: "r"(1 + myTile), "r"(32 * myParts) : "memory");
                             if (sp == s && gi < nG && !(tiled && myIdle)) {
                                 // rows x .. x+B-1 (x a multiple of B, planes padded to a multiple of 4): aligned pairs, rows beyond Lg are padding
 #pragma unroll
@@ -1027,7 +1058,7 @@ __global__ void __launch_bounds__(NT, (TSMEM && NT == FB_THREADS) ? FB_CTAS : 1)
                                         *cp = v;
                                     }
                             }
-                            if (tiled) { __syncthreads(); if (sp == 0) PHASE(3); }
+                            if (tiled && !tileBar) { __syncthreads(); if (sp == 0) PHASE(3); }
                         }
                         if (tiled) break;
                     }

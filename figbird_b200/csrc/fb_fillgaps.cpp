@@ -6,7 +6,7 @@
 //     cost-balanced over the visible GPUs (FIGBIRD_GPUS), one engine context per GPU, no collective;
 //   * every gap runs its sequential control logic on a fiber of a small worker pool; the device requests of all
 //     gaps in flight on a lane are merged into one fb_em_run per tick (LaneQueue below);
-//   * draw.txt is written in gap order (the reference concatenates it in worker order, FillGaps.cpp:222-258).
+//   * draw.txt is written once, in the order the reference's per-worker files would have been concatenated (referenceDrawOrder below).
 #include <algorithm>
 #include <atomic>
 #include <chrono>
