@@ -50,15 +50,19 @@ WORKLOADS = {
     # library, unmapped mode on the 3500 bp jump library (maxDistance 4025).  Same seed and gap spacing => the same draft for both.
     "c3": {"partial": ({"genome": 4600000, "scaffolds": 10, "gaps": 500, "gapmin": 10, "gapmax": 500, "cov": 50, "sd": 20, "minsep": 4175, "near": 700, "model-pairs": 300000}, 100, 200),
            "unmapped": ({"genome": 4600000, "scaffolds": 10, "gaps": 500, "gapmin": 10, "gapmax": 500, "cov": 20, "sd": 350, "minsep": 4175}, 100, 3500)},
+    # BASELINE configs[4] regime at single-GPU size: gaps of 10-5000 bp of which 5 % are negative-overlap gaps, two libraries (2x150 @ 500
+    # at 40x for partial mode, 2x150 @ 3500 at 15x for unmapped mode); 600 gaps on 9 Mbp instead of 50 k gaps on 250 Mbp
+    "c5s": {"partial": ({"genome": 9000000, "scaffolds": 6, "gaps": 600, "gapmin": 10, "gapmax": 5000, "cov": 40, "sd": 50, "minsep": 4250, "negfrac": 0.05, "near": 900, "model-pairs": 300000}, 150, 500),
+            "unmapped": ({"genome": 9000000, "scaffolds": 6, "gaps": 600, "gapmin": 10, "gapmax": 5000, "cov": 15, "sd": 350, "minsep": 4250, "negfrac": 0.05}, 150, 3500)},
     "c1": ({"genome": 1000000, "scaffolds": 4, "gaps": 50, "gapmin": 10, "gapmax": 500, "cov": 30, "sd": 20, "near": 700, "model-pairs": 150000}, 100, 200),
     "tiny": ({"genome": 80000, "scaffolds": 1, "gaps": 8, "gapmin": 5, "gapmax": 300, "cov": 30, "sd": 20}, 100, 200),
 }
-SEEDS = {"c4": 104, "c2": 102, "c3": 103, "c2n": 102, "c4s": 102, "c1": 101, "tiny": 7}
+SEEDS = {"c4": 104, "c2": 102, "c3": 103, "c5s": 105, "c2n": 102, "c4s": 102, "c1": 101, "tiny": 7}
 # bounded samples of a workload for the CPU reference: same generator parameters (gap lengths, reads, coverage, density of gaps)
 # on a shorter draft.  (gaps for the reference arm, gaps for the in-line cpu_baseline of our arm)
 # (a C4 gap is ~2e7 placements = about a core-minute of the as-shipped worker, the heaviest ones several: samples stay small so that
 #  the reference arm -- count, one as-shipped step, one steady-state step -- ends within ten minutes on 16 cores)
-SAMPLE_GAPS = {"c4": (32, 16), "c4s": (32, 16), "c2": (500, 32), "c3": (64, 16), "c2n": (500, 32), "c1": (50, 16), "tiny": (8, 8)}
+SAMPLE_GAPS = {"c4": (32, 16), "c4s": (32, 16), "c2": (500, 32), "c3": (64, 16), "c5s": (32, 16), "c2n": (500, 32), "c1": (50, 16), "tiny": (8, 8)}
 
 
 def gen_of(workload):
@@ -217,6 +221,22 @@ def run_step_reference(case, threads):
 def steady_reference(case, cores, worker):
     import fbcase as fc
     return sum(fc.run_reference_workers_parallel(mode_case(case, mode), mode, cores, worker) for mode in ("partial", "unmapped"))
+
+
+def cpu_baseline(workload, base, cores, unit):
+    """The reference's FillGaps as shipped on a small seeded sample of the workload, all host cores (the in-line `cpu_baseline`)."""
+    ng = SAMPLE_GAPS[workload][1]
+    sample = prepare_case(os.path.join(base, "%s_sample%d" % (workload, ng)), sample_spec(workload, ng), SEEDS[workload] + 2000)
+    placements = count_reference_placements(sample, cores, "%s_sample%d_seed%d" % (workload, ng, SEEDS[workload] + 2000))
+    secs = run_step_reference(sample, cores)
+    out = {"value": placements / secs, "unit": unit, "cores": cores, "kind": "reference",
+           "sample": "%d-gap sample of the %s workload (same generator parameters), FillGaps partial+unmapped, as-shipped -O0 worker, numthreads=%d, %.1f s; placements by the reference's own counters" % (ng, workload, cores, secs)}
+    if os.environ.get("FB_BENCH_FULL_BASELINE"):      # the steady-state and -O2 flavours (minutes more; the reference arm reports the former)
+        steady = steady_reference(sample, cores, "figbird_worker_O0")
+        tuned = steady_reference(sample, cores, "figbird_worker_O2")
+        out["steady_state"] = {"value": placements / steady, "seconds": steady, "note": "same sample, %d as-shipped -O0 worker processes started together (no driver sleep, no run-time compile)" % min(cores, ng)}
+        out["tuned"] = {"value": placements / tuned, "seconds": tuned, "note": "same, worker built -O2 -D_FORTIFY_SOURCE=0 (plain -O2 aborts, SURVEY 5)"}
+    return out
 
 
 def gaps_of(case):
@@ -428,17 +448,10 @@ def main():
                 ps["different_" + mode] = sorted(bad)[:20]
         line["parity_sample"] = ps
     if world == 1 and not a.no_cpu_baseline and fc.have_reference():
-        ng = SAMPLE_GAPS[a.workload][1]
-        sample = prepare_case(os.path.join(base, "%s_sample%d" % (a.workload, ng)), sample_spec(a.workload, ng), SEEDS[a.workload] + 2000)
-        placements = count_reference_placements(sample, cores, "%s_sample%d_seed%d" % (a.workload, ng, SEEDS[a.workload] + 2000))
-        secs = run_step_reference(sample, cores)
-        line["cpu_baseline"] = {"value": placements / secs, "unit": unit, "cores": cores, "kind": "reference",
-                                "sample": "%d-gap sample of the %s workload (same generator parameters), FillGaps partial+unmapped, as-shipped -O0 worker, numthreads=%d, %.1f s; placements by the reference's own counters" % (ng, a.workload, cores, secs)}
-        if os.environ.get("FB_BENCH_FULL_BASELINE"):      # the steady-state and -O2 flavours (minutes more; the reference arm reports the former)
-            steady = steady_reference(sample, cores, "figbird_worker_O0")
-            tuned = steady_reference(sample, cores, "figbird_worker_O2")
-            line["cpu_baseline"]["steady_state"] = {"value": placements / steady, "seconds": steady, "note": "same sample, %d as-shipped -O0 worker processes started together (no driver sleep, no run-time compile)" % min(cores, ng)}
-            line["cpu_baseline"]["tuned"] = {"value": placements / tuned, "seconds": tuned, "note": "same, worker built -O2 -D_FORTIFY_SOURCE=0 (plain -O2 aborts, SURVEY 5)"}
+        try:
+            line["cpu_baseline"] = cpu_baseline(a.workload, base, cores, unit)
+        except Exception as e:      # the baseline is a side measurement: its failure must not cost the bench line
+            line["cpu_baseline"] = {"value": None, "unit": unit, "cores": cores, "kind": "reference", "sample": "failed: %s" % str(e)[:300]}
     emit(line)
     if dist is not None:
         dist.destroy_process_group()
