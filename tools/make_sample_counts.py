@@ -17,7 +17,7 @@ def main():
     known = json.load(open(dst)) if os.path.exists(dst) else {}
     cores = os.cpu_count() or 1
     for w in (sys.argv[1:] or ["c4"]):
-        for ng, off in ((bench.SAMPLE_GAPS[w][0], 1000), (bench.SAMPLE_GAPS[w][1], 2000)):
+        for ng, off in sorted(set(((bench.SAMPLE_GAPS[w][0], 2000), (bench.SAMPLE_GAPS[w][1], 2000)))):
             if ng >= bench.gen_of(w)["gaps"]:
                 continue
             key = "%s_sample%d_seed%d" % (w, ng, bench.SEEDS[w] + off)
