@@ -25,6 +25,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <map>
 #include <mutex>
 #include <string>
@@ -556,14 +557,20 @@ bool writeWhole(const std::string& path, const std::string& data) {
     return true;
 }
 
+// (an exception on a worker thread -- out of memory, say -- is carried to the caller, which turns it into exit status 1)
 template <class F>
 void parallelFor(size_t n, int threads, F f) {
     threads = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, n));
     if (threads <= 1) { for (size_t i = 0; i < n; i++) f(i); return; }
     std::atomic<size_t> next(0);
     std::vector<std::thread> th;
-    for (int t = 0; t < threads; t++) th.emplace_back([&] { for (size_t i; (i = next++) < n;) f(i); });
+    std::mutex emu; std::exception_ptr err;
+    for (int t = 0; t < threads; t++) th.emplace_back([&] {
+        try { for (size_t i; (i = next++) < n;) f(i); }
+        catch (...) { std::lock_guard<std::mutex> l(emu); if (!err) err = std::current_exception(); next = n; }
+    });
     for (auto& t : th) t.join();
+    if (err) std::rethrow_exception(err);
 }
 
 struct Mapped {

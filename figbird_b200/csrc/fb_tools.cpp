@@ -9,6 +9,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <stdexcept>
 #include <string>
 #include <vector>
 #include <fcntl.h>
@@ -280,7 +282,8 @@ int preprocessMain(int argc, const char* const* argv);      // fb_preprocess.cpp
 
 #define FB_TOOL_ENTRY(name, fn) \
     extern "C" int32_t name(int32_t argc, const char* const* argv) { \
-        try { return fb::fn(argc, argv); } catch (const std::exception& e) { fprintf(stderr, "figbird_b200: %s\n", e.what()); return 1; } }
+        try { return fb::fn(argc, argv); } catch (const std::exception& e) { fprintf(stderr, "figbird_b200: %s\n", e.what()); return 1; } \
+        catch (...) { fprintf(stderr, "figbird_b200: tool failed\n"); return 1; } }
 FB_TOOL_ENTRY(fb_combinegaps_main, combineGapsMain)
 FB_TOOL_ENTRY(fb_flanktrim_main, flankTrimMain)
 FB_TOOL_ENTRY(fb_reduce_scf_main, reduceScfMain)
