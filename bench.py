@@ -244,6 +244,95 @@ def gaps_of(case):
     return len(open(os.path.join(mode_case(case, "partial"), "partial", "Temp", "gapInfo.txt")).readlines())
 
 
+def assemble_line(a, world, metrics, dt_max, clk, mb, sm_count, ngaps, work, unit, metric, config, t_prep):
+    """The JSON line of our arm from the per-call metrics of the timed steps (everything that needs no GPU: tests/test_bench_cpu.py
+    runs it on recorded metrics)."""
+    S = max(a.steps, 1)
+    dev_ms = sum(m["device_ms"] for m in metrics)                 # busiest GPU per FillGaps call, summed
+    per_gpu = [sum(m["device_ms_per_gpu"][i] for m in metrics) for i in range(len(metrics[0]["device_ms_per_gpu"]))] if metrics else []
+    dev_p1 = sum(m["dev_placements_p1"] for m in metrics); dev_p2 = sum(m["dev_placements_p2"] for m in metrics)
+    ref_p1 = sum(m["ref_placements_p1"] for m in metrics)
+    terms = sum(m["dev_base_terms"] for m in metrics)
+    launches = sum(m["kernel_launches"] for m in metrics)
+    h2d = sum(m["h2d_bytes"] for m in metrics); d2h = sum(m["d2h_bytes"] for m in metrics)
+    # ---- roofline of the dominant (only) kernel fb_em_kernel: FP64 pipe, no-FMA ceiling (mb = fb_microbench_fp64 on this GPU)
+    # algorithmic FP64 ops = 4 per pass-1 base term + 1 per pass-2 base term.  base_terms counts both passes; pass 1 and pass 2 score
+    # the same (read, offset) pairs, so split by placements.  Kernel time = sum over GPUs of each GPU's busy time (union of its kernel
+    # intervals): the figure is per GPU.
+    t1 = terms * dev_p1 / max(dev_p1 + dev_p2, 1); t2 = terms - t1
+    flops = 4.0 * t1 + 1.0 * t2
+    busy_ms = sum(per_gpu) if per_gpu else dev_ms
+    ach = flops / (busy_ms * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    lane1 = sum(m.get("lane_steps_p1", 0) for m in metrics); lane2 = sum(m.get("lane_steps_p2", 0) for m in metrics)
+    ncu = {}
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
+    except Exception:
+        pass
+    dom = ncu.get("unmapped", {})
+    smem_peak = 128.0 * sm_count * (clk["sm_mhz"] or 1965.0) * 1e6 / 1e9
+    roof = {"bound": "fp64-issue",
+            "bound_note": "neither HBM- nor tensor-bound (SURVEY.md 8d): FP64 issue without FMA (4 separately rounded ops per pass-1 term as the reference computes them); "
+                          "co-limited by the shared-memory crossbar: one 16-byte table entry per gap-row term (DESIGN.md 3)",
+            "achieved": ach, "peak": mb["dmul_tinstr_s"], "unit": "TFLOP/s", "frac": ach / mb["dmul_tinstr_s"] if mb["dmul_tinstr_s"] else None,
+            "per": "GPU (algorithmic flop of all GPUs / summed per-GPU kernel time)",
+            "traffic": dom.get("dram_bytes_per_launch"),
+            "traffic_note": ("dram__bytes_read+write of the dominant fb_em_kernel launch (ncu --set full, profiles/ncu_summary.json: %s, grid %s, %.1f ms); algorithmic HBM bytes of that launch ~= inputs once + result arena"
+                             % (dom.get("file"), dom.get("grid"), dom.get("duration_ms", 0.0))) if dom else None,
+            "peak_source": "fb_microbench_fp64 on this GPU (DMUL chains, 1 flop/instr); DFMA rate %.1f TFLOP/s" % mb["dfma_tflops"],
+            "algorithmic": "4 FP64 ops per pass-1 base term, 1 per pass-2 base term (SURVEY.md 8d); %.3e base terms per step" % (terms / S),
+            "kernel_ms_per_launch": busy_ms / max(launches, 1),
+            "executed_vs_algorithmic": {"pass1_lane_steps": lane1, "pass2_lane_steps": lane2, "algorithmic_terms_pass1": t1, "algorithmic_terms_pass2": t2,
+                                        "note": "flank terms come from the per-gap cache and pass 2 is pruned, so the kernel walks fewer terms than the reference evaluates"},
+            "smem": {"achieved_gbs": 16.0 * lane1 / (busy_ms * 1e-3) / 1e9, "peak_gbs": smem_peak, "frac": 16.0 * lane1 / (busy_ms * 1e-3) / 1e9 / smem_peak,
+                     "note": "pass-1 walk only: 16 B (LDS.128 of {P, E-P}) per executed gap-row lane step / kernel time, against 128 B/clk/SM x SMs x SM clock"},
+            "ncu": {k: dom.get(k) for k in ("issue_active_pct", "smem_wavefronts_pct", "fp64_pipe_pct", "alu_pipe_pct", "lsu_pipe_pct", "warps_active_pct", "stall_barrier")} if dom else None,
+            # the busiest unit of the dominant launches according to ncu (committed capture, not this run): the shared-memory pipe
+            "smem_pipe": ({"achieved": dom.get("smem_wavefronts_pct"), "peak": 100.0, "unit": "%% of peak shared-memory wavefronts (ncu l1tex__data_pipe_lsu_wavefronts_mem_shared, dominant launch of profiles/%s)" % dom.get("file"),
+                           "frac": (dom.get("smem_wavefronts_pct") or 0.0) / 100.0} if dom else None),
+            "hbm": {"achieved_gbs": (h2d + d2h) / (busy_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                    "note": "algorithmic HBM bytes ~= result arena + inputs; tables live in shared memory"}}
+    host = {k: sum(m[k] for m in metrics) / S for k in ("t_load", "t_model", "t_model_wait", "t_prepare", "t_fill", "t_write", "t_ctx_upload", "t_workers", "t_engine_calls", "cpu_workers") if metrics and k in metrics[0]}
+    wall = dt_max / S
+    parts = {"kernels (busiest GPU)": dev_ms * 1e-3 / S,
+             "GPU idle inside the fill phase (host replay between engine calls, tail, imbalance across GPUs)": max(0.0, host.get("t_fill", 0) - dev_ms * 1e-3 / S),
+             "serial host phases (load, prepare, write, python glue)": max(0.0, wall - host.get("t_fill", 0))}
+    limiter = max(parts, key=parts.get)
+    line = {"metric": metric, "value": ref_p1 / (dev_ms * 1e-3), "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * wall, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config, "clocks": clk,
+            "e2e": {"value": ref_p1 / dt_max, "unit": unit, "h2d_bytes_per_step": h2d / S, "d2h_bytes_per_step": d2h / S,
+                    "note": "through fb_fillgaps_main: files -> model -> per-gap control on host fibers -> engine -> files; reference-equivalent pass-1 placements / wall",
+                    "gaps_per_s": ngaps * S / dt_max, "gaps": ngaps, "seconds_per_step": wall,
+                    "seconds_per_step_breakdown": parts, "limiter": limiter,
+                    "host_seconds_per_step": host, "device_ms_per_gpu_per_step": [x / S for x in per_gpu]},
+            "gpu_launches": int(launches), "placements": {"reference_equivalent_p1": ref_p1, "device_p1": dev_p1, "device_p2": dev_p2,
+                                                          "note": "device counts include speculative candidates past the reference's early exits"},
+            "value_device_placements": dev_p1 / (dev_ms * 1e-3), "data_prep_s": t_prep, "roofline": roof}
+    # at-size parity: the gapout.txt lines of the last step against the reference worker's lines for a seeded sample of the gaps
+    # (tests/golden/<workload>_sample.json, made by tools/make_sample_expect.py where the reference binaries run)
+    exp_path = os.path.join(ROOT, "tests", "golden", "%s_sample.json" % a.workload)
+    if os.path.exists(exp_path):
+        exp = json.load(open(exp_path))
+        ps = {"gaps_sampled": len(exp["gaps"]), "of": ngaps, "reference": "oracle/_ref %s on the same seeded case" % exp.get("worker", "worker")}
+        for mode in ("partial", "unmapped"):
+            ours = {}
+            for ln in open(os.path.join(work, mode, "Temp", "gapout.txt")):
+                ours[ln.split("\t", 1)[0]] = ln
+            ps["identical_" + mode] = sum(1 for g, ln in exp[mode].items() if ours.get(g) == ln)
+            bad = [int(g) for g, ln in exp[mode].items() if ours.get(g) != ln]
+            if bad:
+                ps["different_" + mode] = sorted(bad)[:20]
+        line["parity_sample"] = ps
+    return line
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -365,92 +454,10 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    S = max(a.steps, 1)
-    dev_ms = sum(m["device_ms"] for m in metrics)                 # busiest GPU per FillGaps call, summed
-    per_gpu = [sum(m["device_ms_per_gpu"][i] for m in metrics) for i in range(len(metrics[0]["device_ms_per_gpu"]))] if metrics else []
-    dev_p1 = sum(m["dev_placements_p1"] for m in metrics); dev_p2 = sum(m["dev_placements_p2"] for m in metrics)
-    ref_p1 = sum(m["ref_placements_p1"] for m in metrics)
-    terms = sum(m["dev_base_terms"] for m in metrics)
-    launches = sum(m["kernel_launches"] for m in metrics)
-    h2d = sum(m["h2d_bytes"] for m in metrics); d2h = sum(m["d2h_bytes"] for m in metrics)
-    ngaps = gaps_of(case)
-
-    # ---- roofline of the dominant (only) kernel fb_em_kernel: FP64 pipe, no-FMA ceiling
     from figbird_b200 import capi
     eng = capi.Engine(0)
     mb = eng.microbench_fp64(); eng.close()
-    # algorithmic FP64 ops = 4 per pass-1 base term + 1 per pass-2 base term.  base_terms counts both passes; pass 1 and pass 2 score
-    # the same (read, offset) pairs, so split by placements.  Kernel time = sum over GPUs of each GPU's busy time (union of its kernel
-    # intervals): the figure is per GPU.
-    t1 = terms * dev_p1 / max(dev_p1 + dev_p2, 1); t2 = terms - t1
-    flops = 4.0 * t1 + 1.0 * t2
-    busy_ms = sum(per_gpu) if per_gpu else dev_ms
-    ach = flops / (busy_ms * 1e-3) / 1e12
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    lane1 = sum(m.get("lane_steps_p1", 0) for m in metrics); lane2 = sum(m.get("lane_steps_p2", 0) for m in metrics)
-    ncu = {}
-    try:
-        ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
-    except Exception:
-        pass
-    dom = ncu.get("unmapped", {})
-    clk = sampler.summary()
-    smem_peak = 128.0 * torch.cuda.get_device_properties(0).multi_processor_count * (clk["sm_mhz"] or 1965.0) * 1e6 / 1e9
-    roof = {"bound": "fp64-issue",
-            "bound_note": "neither HBM- nor tensor-bound (SURVEY.md 8d): FP64 issue without FMA (4 separately rounded ops per pass-1 term as the reference computes them); "
-                          "co-limited by the shared-memory crossbar: one 16-byte table entry per gap-row term (DESIGN.md 3)",
-            "achieved": ach, "peak": mb["dmul_tinstr_s"], "unit": "TFLOP/s", "frac": ach / mb["dmul_tinstr_s"] if mb["dmul_tinstr_s"] else None,
-            "per": "GPU (algorithmic flop of all GPUs / summed per-GPU kernel time)",
-            "traffic": dom.get("dram_bytes_per_launch"),
-            "traffic_note": ("dram__bytes_read+write of the dominant fb_em_kernel launch (ncu --set full, profiles/ncu_summary.json: %s, grid %s, %.1f ms); algorithmic HBM bytes of that launch ~= inputs once + result arena"
-                             % (dom.get("file"), dom.get("grid"), dom.get("duration_ms", 0.0))) if dom else None,
-            "peak_source": "fb_microbench_fp64 on this GPU (DMUL chains, 1 flop/instr); DFMA rate %.1f TFLOP/s" % mb["dfma_tflops"],
-            "algorithmic": "4 FP64 ops per pass-1 base term, 1 per pass-2 base term (SURVEY.md 8d); %.3e base terms per step" % (terms / S),
-            "kernel_ms_per_launch": busy_ms / max(launches, 1),
-            "executed_vs_algorithmic": {"pass1_lane_steps": lane1, "pass2_lane_steps": lane2, "algorithmic_terms_pass1": t1, "algorithmic_terms_pass2": t2,
-                                        "note": "flank terms come from the per-gap cache and pass 2 is pruned, so the kernel walks fewer terms than the reference evaluates"},
-            "smem": {"achieved_gbs": 16.0 * lane1 / (busy_ms * 1e-3) / 1e9, "peak_gbs": smem_peak, "frac": 16.0 * lane1 / (busy_ms * 1e-3) / 1e9 / smem_peak,
-                     "note": "pass-1 walk only: 16 B (LDS.128 of {P, E-P}) per executed gap-row lane step / kernel time, against 128 B/clk/SM x SMs x SM clock"},
-            "ncu": {k: dom.get(k) for k in ("issue_active_pct", "smem_wavefronts_pct", "fp64_pipe_pct", "alu_pipe_pct", "lsu_pipe_pct", "warps_active_pct", "stall_barrier")} if dom else None,
-            "hbm": {"achieved_gbs": (h2d + d2h) / (busy_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                    "note": "algorithmic HBM bytes ~= result arena + inputs; tables live in shared memory"}}
-    host = {k: sum(m[k] for m in metrics) / S for k in ("t_load", "t_model", "t_model_wait", "t_prepare", "t_fill", "t_write", "t_ctx_upload", "t_workers", "t_engine_calls", "cpu_workers") if metrics and k in metrics[0]}
-    wall = dt_max / S
-    parts = {"kernels (busiest GPU)": dev_ms * 1e-3 / S,
-             "GPU idle inside the fill phase (host replay between engine calls, tail, imbalance across GPUs)": max(0.0, host.get("t_fill", 0) - dev_ms * 1e-3 / S),
-             "serial host phases (load, prepare, write, python glue)": max(0.0, wall - host.get("t_fill", 0))}
-    limiter = max(parts, key=parts.get)
-    line = {"metric": metric, "value": ref_p1 / (dev_ms * 1e-3), "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": 1e3 * wall, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config, "clocks": clk,
-            "e2e": {"value": ref_p1 / dt_max, "unit": unit, "h2d_bytes_per_step": h2d / S, "d2h_bytes_per_step": d2h / S,
-                    "note": "through fb_fillgaps_main: files -> model -> per-gap control on host fibers -> engine -> files; reference-equivalent pass-1 placements / wall",
-                    "gaps_per_s": ngaps * S / dt_max, "gaps": ngaps, "seconds_per_step": wall,
-                    "seconds_per_step_breakdown": parts, "limiter": limiter,
-                    "host_seconds_per_step": host, "device_ms_per_gpu_per_step": [x / S for x in per_gpu]},
-            "gpu_launches": int(launches), "placements": {"reference_equivalent_p1": ref_p1, "device_p1": dev_p1, "device_p2": dev_p2,
-                                                          "note": "device counts include speculative candidates past the reference's early exits"},
-            "value_device_placements": dev_p1 / (dev_ms * 1e-3), "data_prep_s": t_prep, "roofline": roof}
-    # at-size parity: the gapout.txt lines of the last step against the reference worker's lines for a seeded sample of the gaps
-    # (tests/golden/<workload>_sample.json, made by tools/make_sample_expect.py where the reference binaries run)
-    exp_path = os.path.join(ROOT, "tests", "golden", "%s_sample.json" % a.workload)
-    if os.path.exists(exp_path):
-        exp = json.load(open(exp_path))
-        ps = {"gaps_sampled": len(exp["gaps"]), "of": ngaps, "reference": "oracle/_ref %s on the same seeded case" % exp.get("worker", "worker")}
-        for mode in ("partial", "unmapped"):
-            ours = {}
-            for ln in open(os.path.join(work, mode, "Temp", "gapout.txt")):
-                ours[ln.split("\t", 1)[0]] = ln
-            ps["identical_" + mode] = sum(1 for g, ln in exp[mode].items() if ours.get(g) == ln)
-            bad = [int(g) for g, ln in exp[mode].items() if ours.get(g) != ln]
-            if bad:
-                ps["different_" + mode] = sorted(bad)[:20]
-        line["parity_sample"] = ps
+    line = assemble_line(a, world, metrics, dt_max, sampler.summary(), mb, torch.cuda.get_device_properties(0).multi_processor_count, gaps_of(case), work, unit, metric, config, t_prep)
     if world == 1 and not a.no_cpu_baseline and fc.have_reference():
         try:
             line["cpu_baseline"] = cpu_baseline(a.workload, base, cores, unit)
