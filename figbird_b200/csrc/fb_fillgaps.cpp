@@ -165,6 +165,9 @@ static void laneWorker(LaneQueue& q, LaneWork& lw, int cap) {
     auto retire = [&](Fiber* f) {
         if (!f->error.empty()) { std::lock_guard<std::mutex> l(lw.emu); if (lw.error.empty()) lw.error = f->error; }
         else (*lw.results)[f->gap] = std::move(f->result);
+        // the gap's working set (reads, tables, strings) is freed here, beside the kernels of the other lane, instead of in one serial
+        // sweep after the last gap (0.1-0.2 s per call at 10 k gaps); nothing reads it once run() has returned
+        (*lw.fills)[f->gap].reset();
         freeStacks.push_back(f->stack);
         delete f;
     };
