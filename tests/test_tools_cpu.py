@@ -11,6 +11,7 @@ import hashlib
 import json
 import os
 import random
+import re
 import shutil
 import subprocess
 import tarfile
@@ -307,3 +308,93 @@ def test_tools_through_the_c_abi(tmp_path):
     assert open(str(tmp_path / "t.fa")).read().split("\n")[1][196:208] == "ACNNNNNNNNGT"
     assert capi.tool("reduce_scf", [str(tmp_path / "missing.fa"), str(tmp_path) + "/"]) == 1
     assert capi.tool("preprocess", ["too", "few"]) == 1
+
+
+@needs_ref
+def test_preprocess_on_bowtie2_like_oddities(cases, tmp_path):
+    """What the generator never writes but bowtie2 does: PCR duplicates (exact, and the same read minus a base or two at an end --
+    the mode-2 filter drops a read whose core is contained in a stored one), insertions spanning the gap ("aMbIcM": the MIM evidence
+    of stat2.txt), soft clips at both ends, lower-case and N bases, more than 3001 reads for one gap (the cap), blanks inside a tag."""
+    case = cases["frag"]
+    pr = fc.case_params(case)
+    work = tmp_path / "case"; work.mkdir()
+    shutil.copy(os.path.join(case, "draft.fa"), str(work / "draft.fa"))
+    rng = random.Random(17)
+    for sam in ("result1.sam", "result2.sam"):
+        lines = open(os.path.join(case, sam)).read().split("\n")
+        pairs, head = [], []
+        i = 0
+        while i + 1 < len(lines):
+            if lines[i].startswith("@") or not lines[i]:
+                head.append(lines[i]); i += 1; continue
+            pairs.append((lines[i], lines[i + 1])); i += 2
+        out = []
+        n = 0
+        for a, b in pairs:
+            fa_, fb_ = a.split("\t"), b.split("\t")
+            interesting = (int(fa_[1]) & 2) == 0 or "S" in fa_[5] or "S" in fb_[5]
+            out.append((a, b))
+            if not interesting:
+                continue
+            r = rng.random()
+            n += 1
+            nm = "dup%d" % n
+            if r < 0.10:                                     # exact duplicate under another name
+                out.append(("\t".join([nm] + fa_[1:]), "\t".join([nm] + fb_[1:])))
+            elif r < 0.20:                                   # the same pair, both reads two bases shorter at both ends (contained cores)
+                def trim(f):
+                    g = list(f)
+                    if g[5] != "*" and g[5].endswith("M") and g[5][:-1].isdigit():
+                        g[5] = "%dM" % (int(g[5][:-1]) - 4); g[3] = str(int(g[3]) + 2)
+                    elif g[5] != "*":
+                        return f
+                    g[9] = g[9][2:-2]; g[10] = g[10][2:-2]
+                    return g
+                out.append(("\t".join([nm] + trim(fa_)[1:]), "\t".join([nm] + trim(fb_)[1:])))
+            elif r < 0.30 and any(re.match(r"^\d+M\d+S$", f[5]) and int(re.match(r"^\d+M(\d+)S$", f[5]).group(1)) > 14 for f in (fa_, fb_)):
+                # a read that runs into the gap from the left and comes out on the other side: "aMbIcM", the MIM evidence
+                ga, gb = list(fa_), list(fb_)
+                for g in (ga, gb):
+                    m = re.match(r"^(\d+)M(\d+)S$", g[5])
+                    if m and int(m.group(2)) > 14:
+                        g[5] = "%sM%dI10M" % (m.group(1), int(m.group(2)) - 10)
+                        g[9] = ("C" if g[9][0] != "C" else "G") + g[9][1:]      # (an exact copy would be dropped as a duplicate)
+                out.append(("\t".join([nm] + ga[1:]), "\t".join([nm] + gb[1:])))
+            elif r < 0.32 and "S" in fa_[5]:                 # soft clips at both ends
+                g = list(fa_); L = len(g[9])
+                g[5] = "7S%dM9S" % (L - 16)
+                out.append(("\t".join([nm] + g[1:]), "\t".join([nm] + fb_[1:])))
+            elif r < 0.36:                                   # lower-case bases and an N
+                g = list(fb_); g[9] = g[9][:10].lower() + "N" + g[9][11:]
+                out.append(("\t".join([nm] + fa_[1:]), "\t".join([nm] + g[1:])))
+            elif r < 0.40:                                   # a blank inside an optional field: getSAM splits on blanks too
+                out.append((a + "\tXX:Z:two words", "\t".join([nm.replace("dup", "dupb")] + fb_[1:]).replace(nm.replace("dup", "dupb"), fa_[0], 1)))
+        # more than 3001 candidates for one gap: one interesting pair repeated with distinct reads
+        if sam == "result2.sam":
+            seed_pair = next(((a, b) for a, b in pairs if (int(a.split("\t")[1]) & 6) == 0 and (int(b.split("\t")[1]) & 4) != 0), None)
+        else:
+            seed_pair = next(((a, b) for a, b in pairs if "S" in a.split("\t")[5] and (int(a.split("\t")[1]) & 2)), None)
+        if seed_pair:
+            fa_, fb_ = seed_pair[0].split("\t"), seed_pair[1].split("\t")
+            for k in range(3100):
+                s = "".join(rng.choice("ACGT") for _ in range(len(fb_[9])))
+                if sam == "result2.sam":
+                    out.append(("\t".join(["cap%d" % k] + fa_[1:]), "\t".join(["cap%d" % k] + fb_[1:9] + [s] + fb_[10:])))
+                else:
+                    s1 = "".join(rng.choice("ACGT") for _ in range(len(fa_[9])))
+                    out.append(("\t".join(["cap%d" % k] + fa_[1:9] + [s1] + fa_[10:]), "\t".join(["cap%d" % k] + fb_[1:])))
+        with open(str(work / sam), "w") as f:
+            f.write("\n".join([h for h in head if h] + [x for p in out for x in p]) + "\n")
+    for mode, x in (("partial", pr["x1"]), ("unmapped", pr["x2"])):
+        ref = str(tmp_path / ("ref_" + mode))
+        run_ref_preprocess(str(work), mode, ref, x)
+        for env in ({"FIGBIRD_PP_BLOCK": "20000"}, {"FIGBIRD_PP_SEQUENTIAL": "1"}):
+            ours = str(tmp_path / ("ours_" + mode))
+            run_ours_preprocess(str(work), mode, ours, x, env=env)
+            compare_dirs(ref, ours, mode)
+        if mode == "partial":
+            s2 = [l.split("\t") for l in open(os.path.join(ref, "Temp", "stat2.txt")).read().strip().split("\n")]
+            assert any(l[1] == "1" for l in s2), "no MIM evidence was generated: the test lost its point"
+        pat = "partial_gaps_*.sam" if mode == "partial" else "gaps_*.sam"
+        per = 1 if mode == "partial" else 2
+        assert max(open(p, "rb").read().count(b"\n") for p in glob.glob(os.path.join(ref, "Gaps", pat))) >= 3001 * per - 1
