@@ -364,12 +364,24 @@ int fillgapsMain(int argc, const char* const* argv) {
     const int ioThreads = std::max(1, std::min(a.numThreads > 0 ? a.numThreads : 1, 64));
     int hostThreads = std::max(ioThreads, (int)std::thread::hardware_concurrency());
     if (const char* e = getenv("FIGBIRD_HOST_THREADS")) hostThreads = std::max(1, atoi(e));     // several ranks on one host share its cores
+    // per-gap inputs: the text files of the contract, or -- only when the caller asks for it (FIGBIRD_CONTAINER=1) and fb_preprocess_main
+    // left them -- the containers that hold the same bytes in one mapped file each
+    GapContainer partialBox, unmappedBox;
+    if (const char* e = getenv("FIGBIRD_CONTAINER")) if (atoi(e) != 0) {
+        partialBox.open(a.gapsDir + "partial_gaps.fbc", 1, (size_t)totGaps);
+        if (a.unmapped == 1) unmappedBox.open(a.gapsDir + "gaps.fbc", 2, (size_t)totGaps);
+    }
     std::atomic<long long> tIo(0), tCtor(0), tPrep(0);
     parallelFor(nG, hostThreads, [&](int g) {
         auto x0 = clk::now();
         GapInput in; in.rec = gaps[g];
-        loadPartial(a.gapsDir + "partial_gaps_" + std::to_string(g) + ".sam", in.partial, in.partialExists);
-        if (a.unmapped == 1) loadUnmapped(a.gapsDir + "gaps_" + std::to_string(g) + ".sam", a.readLength, in.unm, in.unmPairCount);
+        size_t tn = 0;
+        if (partialBox.valid()) { const char* t = partialBox.text((size_t)g, tn); loadPartialText(t, tn, in.partial); in.partialExists = true; }
+        else loadPartial(a.gapsDir + "partial_gaps_" + std::to_string(g) + ".sam", in.partial, in.partialExists);
+        if (a.unmapped == 1) {
+            if (unmappedBox.valid()) { const char* t = unmappedBox.text((size_t)g, tn); loadUnmappedText(t, tn, in.unm, in.unmPairCount); }
+            else loadUnmapped(a.gapsDir + "gaps_" + std::to_string(g) + ".sam", a.readLength, in.unm, in.unmPairCount);
+        }
         auto x1 = clk::now();
         fills[g].reset(new GapFill(a, model, sc, std::move(in)));
         auto x2 = clk::now();

@@ -143,6 +143,7 @@ struct View { const char* p; size_t n; bool empty() const { return n == 0; } };
 struct Records {
     const char* p; const char* e;
     explicit Records(const std::string& t) : p(t.data()), e(t.data() + t.size()) {}
+    Records(const char* b, size_t n) : p(b), e(b + n) {}
     bool next(View& r) {
         if (p >= e) return false;
         const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
@@ -180,7 +181,11 @@ bool loadPartial(const std::string& path, std::vector<PartialRead>& out, bool& e
     FileText ft;
     exists = ft.read(path);
     if (!exists) return false;
-    Records rec(ft.buf);
+    loadPartialText(ft.buf.data(), ft.buf.size(), out);
+    return true;
+}
+void loadPartialText(const char* text, size_t n_, std::vector<PartialRead>& out) {
+    Records rec(text, n_);
     View r, t[7];
     while (rec.next(r)) {
         const int n = fields(r, t, 7);
@@ -195,7 +200,6 @@ bool loadPartial(const std::string& path, std::vector<PartialRead>& out, bool& e
         if (n == 1) { while (!pr.seq.empty() && pr.seq.back() == '\n') pr.seq.pop_back(); }
         if (out.size() > 3000) break;
     }
-    return true;
 }
 
 static char rc(char ch) {   // reverse(), Figbird.cpp:1427-1449
@@ -210,8 +214,12 @@ bool loadUnmapped(const std::string& path, int readLen, std::vector<UnmappedRead
     FileText ft;
     pairCount = 0;
     if (!ft.read(path)) return false;
-    { Records all(ft.buf); View r; size_t n = 0; while (all.next(r)) n++; pairCount = (int)(n / 2); }
-    Records rec(ft.buf);
+    loadUnmappedText(ft.buf.data(), ft.buf.size(), out, pairCount);
+    return true;
+}
+void loadUnmappedText(const char* text, size_t n_, std::vector<UnmappedRead>& out, int& pairCount) {
+    { Records all(text, n_); View r; size_t n = 0; while (all.next(r)) n++; pairCount = (int)(n / 2); }
+    Records rec(text, n_);
     View l1, l2, t1[4], t2[8];
     int total = 0;
     while (rec.next(l1)) {
@@ -230,7 +238,45 @@ bool loadUnmapped(const std::string& path, int readLen, std::vector<UnmappedRead
         } else { u.seq.assign(t2[6].p, t2[6].n); u.isReverse = 0; }
         if (++total == 3000) break;   // unmapped_limit
     }
-    return true;
+}
+
+// ---- per-gap container (opt-in, FIGBIRD_CONTAINER=1): what fb_preprocess_main writes beside the per-gap text files
+// when asked to -- the same bytes, all gaps in one file: "FBGAPS1\0", kind (1 partial_gaps / 2 gaps), number of gaps, nGaps + 1
+// offsets, then the text of gap 0, 1, ...  The text files stay the contract; the container saves a reader 2 x 10^4 opens.
+bool GapContainer::open(const std::string& path, uint32_t kind, size_t nGaps) {
+    close();
+    const int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || (size_t)st.st_size < 16) { ::close(fd); return false; }
+    void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    ::close(fd);
+    if (m == MAP_FAILED) return false;
+    base_ = (const char*)m; size_ = (size_t)st.st_size;
+    uint32_t k = 0, n = 0;
+    memcpy(&k, base_ + 8, 4); memcpy(&n, base_ + 12, 4);
+    const size_t head = 16 + 8 * ((size_t)n + 1);
+    bool ok = memcmp(base_, "FBGAPS1", 8) == 0 && k == kind && (size_t)n == nGaps && head <= size_;
+    if (ok) {
+        off_ = (const uint64_t*)(base_ + 16); n_ = n;
+        for (size_t g = 0; g < n_ && ok; g++) ok = off_[g] <= off_[g + 1];
+        ok = ok && off_[0] == head && off_[n_] == size_;
+    }
+    if (!ok) close();
+    return ok;
+}
+void GapContainer::close() { if (base_) munmap((void*)base_, size_); base_ = nullptr; off_ = nullptr; n_ = 0; size_ = 0; }
+bool writeGapContainer(const std::string& path, uint32_t kind, const std::vector<std::string>& texts) {
+    std::vector<uint64_t> off(texts.size() + 1);
+    const uint64_t head = 16 + 8 * (uint64_t)(texts.size() + 1);
+    off[0] = head;
+    for (size_t g = 0; g < texts.size(); g++) off[g + 1] = off[g] + texts[g].size();
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    const uint32_t n = (uint32_t)texts.size();
+    bool ok = fwrite("FBGAPS1", 1, 8, f) == 8 && fwrite(&kind, 4, 1, f) == 1 && fwrite(&n, 4, 1, f) == 1 && fwrite(off.data(), 8, off.size(), f) == off.size();
+    for (size_t g = 0; g < texts.size() && ok; g++) ok = texts[g].empty() || fwrite(texts[g].data(), 1, texts[g].size(), f) == texts[g].size();
+    return fclose(f) == 0 && ok;
 }
 
 // ---- writers -------------------------------------------------------------------------------------------

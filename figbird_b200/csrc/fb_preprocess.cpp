@@ -39,6 +39,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include "fb_io.h"
 #include "fb_tools.h"
 
 namespace fb {
@@ -807,11 +808,17 @@ int preprocessMain(int argc, const char* const* argv) {
             std::vector<std::string>().swap(st.stored); st.seen.clear(); st.windows.clear();
         });
     }
+    const bool container = getenv("FIGBIRD_CONTAINER") && atoi(getenv("FIGBIRD_CONTAINER")) != 0;
     parallelFor(nGaps, threads, [&](size_t g) {
         const std::string path = gapsDir + (samflag == 2 ? "gaps_" : "partial_gaps_") + std::to_string(g) + ".sam";
         if (!writeWhole(path, states[g].text)) ioOk = false;
-        std::string().swap(states[g].text);
+        if (!container) std::string().swap(states[g].text);
     });
+    if (container) {      // (opt-in) the same bytes once more, all gaps in one file that fb_fillgaps_main maps
+        std::vector<std::string> texts(nGaps);
+        for (size_t g = 0; g < nGaps; g++) texts[g].swap(states[g].text);
+        if (!writeGapContainer(gapsDir + (samflag == 2 ? "gaps.fbc" : "partial_gaps.fbc"), samflag == 2 ? 2u : 1u, texts)) ioOk = false;
+    }
     if (!ioOk) { fprintf(stderr, "figbird_b200: cannot write the per-gap files under %s\n", gapsDir.c_str()); return 1; }
     fprintf(statFile, "%ld %ld %ld %ld", total.totalCount, total.unCount, (long)total.maxReadLength, 5000L);
     for (size_t g = 0; g < nGaps; g++) fprintf(statFile2, "%d\t%d\t%d\n", 1, states[g].perfect, states[g].perfectLen);

@@ -398,3 +398,46 @@ def test_preprocess_on_bowtie2_like_oddities(cases, tmp_path):
         pat = "partial_gaps_*.sam" if mode == "partial" else "gaps_*.sam"
         per = 1 if mode == "partial" else 2
         assert max(open(p, "rb").read().count(b"\n") for p in glob.glob(os.path.join(ref, "Gaps", pat))) >= 3001 * per - 1
+
+
+def test_gap_container_is_the_text_files_in_one_file(tmp_path):
+    """SURVEY 8f-2, opt-in (FIGBIRD_CONTAINER=1): fb_preprocess_main leaves Gaps/partial_gaps.fbc / Gaps/gaps.fbc beside the per-gap text
+    files -- the same bytes behind an offset table -- and fb_fillgaps_main reads its per-gap inputs from them: same outputs."""
+    import struct
+    with tarfile.open(os.path.join(HERE, "golden", "pp1.tar.gz")) as t:
+        t.extractall(str(tmp_path), filter="data")
+    case = str(tmp_path / "pp1")
+    exp = json.load(open(os.path.join(case, "expected.json")))
+    draft = os.path.join(case, "draft.fa")
+    gaps = os.path.join(case, "Gaps") + "/"
+    os.makedirs(gaps)
+    env = dict(os.environ); env["FIGBIRD_CONTAINER"] = "1"
+    for mode, flag, sam in (("partial", "1", "result1.sam"), ("unmapped", "2", "result2.sam")):
+        tmp = os.path.join(case, mode, "Temp") + "/"
+        os.makedirs(tmp)
+        p = subprocess.run([FBTOOL, "preprocess", draft, str(exp["x"][mode]), flag, os.path.join(case, sam), os.path.join(case, mode, "myout.sam"), draft, "r1.fq", "r2.fq", gaps, tmp, "1", "0", "0"], env=env)
+        assert p.returncode == 0
+        box = open(os.path.join(gaps, "partial_gaps.fbc" if mode == "partial" else "gaps.fbc"), "rb").read()
+        kind, n = struct.unpack_from("<II", box, 8)
+        assert box[:8] == b"FBGAPS1\0" and kind == int(flag) and n == len(exp[mode]) - 4
+        off = struct.unpack_from("<%dQ" % (n + 1), box, 16)
+        for g in range(n):
+            assert box[off[g]:off[g + 1]] == open(os.path.join(gaps, ("partial_gaps_%d.sam" if mode == "partial" else "gaps_%d.sam") % g), "rb").read()
+        assert off[n] == len(box)
+    # partial mode through the CPU engine (minutes for unmapped mode at these gap lengths; the loaders are the same code)
+    outs = {}
+    for how in ("text", "container"):
+        tmp = os.path.join(case, "run_" + how, "Temp") + "/"
+        os.makedirs(tmp)
+        for f in ("gapInfo.txt", "stat.txt", "stat2.txt"):
+            shutil.copy(os.path.join(case, "partial", "Temp", f), tmp + f)
+        e = dict(os.environ); e["FIGBIRD_CONTAINER"] = "1" if how == "container" else "0"; e["FIGBIRD_TAIL_ITEMS"] = "0"
+        argv = [draft, str(exp["x"]["partial"]), str(exp["readlen"]), "1", "1", "0", "4", os.path.join(case, "partial", "myout.sam"), tmp, gaps, "30", str(exp["readlen"]), "0", "0", str(exp["insert"])]
+        if how == "container":      # the text files are not even there: everything comes from the container
+            for f in glob.glob(os.path.join(gaps, "partial_gaps_*.sam")):
+                os.remove(f)
+        assert subprocess.run([fc.oracle_exe()] + argv, env=e, stdout=subprocess.DEVNULL).returncode == 0
+        outs[how] = fc.read_outputs(tmp)
+    for f in fc.OUTPUT_FILES:
+        assert outs["text"][f] == outs["container"][f] and outs["text"][f], f
+    assert hashlib.md5(outs["text"]["gapout.txt"]).hexdigest() == exp["fillgaps_partial"]["gapout.txt"]
