@@ -13,6 +13,7 @@
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
@@ -51,7 +52,7 @@ static thread_local Fiber* tlsFiber = nullptr;
 
 class LaneQueue : public DeviceQueue {
 public:
-    LaneQueue(fb_ctx* ctx, int workers) : ctx_(ctx), running_(workers) {}
+    LaneQueue(fb_ctx* ctx, int workers, std::function<std::string()> beforeFirstRun) : ctx_(ctx), running_(workers), beforeFirstRun_(std::move(beforeFirstRun)) {}
     // called on a fiber: park until the lane has run the request
     void submit(int, const std::vector<ItemSpec>& items, std::vector<ItemResult>& results) override {
         Fiber* f = tlsFiber;
@@ -106,13 +107,18 @@ private:
             wi.push_back(w);
         }
         outs_.assign(wi.size(), nullptr);
+        if (beforeFirstRun_) {      // the model: awaited and uploaded here, in front of the lane's first engine call
+            const std::string e = beforeFirstRun_();
+            beforeFirstRun_ = nullptr;
+            if (!e.empty()) { failed_ = true; err_ = e; }
+        }
         auto c0 = std::chrono::steady_clock::now();
         fb_status st = (wi.empty() || failed_) ? FB_OK : fb_em_run(ctx_, wi.data(), (int32_t)wi.size(), outs_.data());
         auto c1 = std::chrono::steady_clock::now();
         tEngine_ += std::chrono::duration<double>(c1 - c0).count();
         if (tickLog_) { if (ticks_ == 0) t0_ = c0; log_.push_back({std::chrono::duration<double>(c0 - t0_).count(), std::chrono::duration<double>(c1 - c0).count(), (int)wi.size(), (int)batch.size()}); }
         ticks_++;
-        if (st != FB_OK) { failed_ = true; err_ = std::string("fb_em_run failed: ") + fb_last_error(ctx_); }
+        if (st != FB_OK && !failed_) { failed_ = true; err_ = std::string("fb_em_run failed: ") + fb_last_error(ctx_); }
         size_t k = 0;
         for (Fiber* f : batch) {
             const size_t n = f->reqItems->size();
@@ -128,6 +134,7 @@ private:
     std::vector<Fiber*> reqs_;
     std::vector<const FbItemOut*> outs_;
     int running_, arrived_ = 0;
+    std::function<std::string()> beforeFirstRun_;
     int64_t gen_ = 0;
     bool failed_ = false; std::string err_;
     int64_t ticks_ = 0;
@@ -463,13 +470,23 @@ int fillgapsMain(int argc, const char* const* argv) {
         B.read_flags = rfl.data(); B.read_jlo = rjlo.data(); B.read_jcut = rjcut.data(); B.n_codes = (int64_t)codes.size(); B.read_codes = codes.data();
         B.n_flank = (int64_t)flank.size(); B.flank_codes = flank.data(); B.n_pile_rows = (int64_t)(pileL.size() / 4); B.pile_left = pileL.data(); B.pile_right = pileR.data();
         if (fb_batch_upload(ctx, &B) != FB_OK) { devErr[d] = std::string("fb_batch_upload: ") + fb_last_error(ctx); fb_ctx_destroy(ctx); return; }
-        if (!waitModel()) { releaseCtx(devs[d], laneOf, ctx); return; }      // reported by the main thread
-        FbModel fm{};
-        fm.max_read_len = model.maxReadLength; fm.err_pos = model.errorPosDist.data(); fm.ins_pos = model.inPosDist.data(); fm.del_pos = model.delPosDist.data();
-        for (int i = 0; i < 5; i++) for (int j = 0; j < 5; j++) fm.err_type[i * 5 + j] = model.errorTypeProbs[i][j];
-        fm.n_insert = model.maxInsertSize; fm.insert_pdf = model.insertPdfSmoothed.data();
-        fm.insert_min = model.insertThresholdMin; fm.insert_max = model.insertThresholdMax; fm.prob_cutoff = model.gapProbCutOff;
-        if (fb_model_upload(ctx, &fm) != FB_OK) { devErr[d] = std::string("fb_model_upload: ") + fb_last_error(ctx); fb_ctx_destroy(ctx); return; }
+        // The model is needed by the first engine call, not before: the gaps' fibers start at once and build their first requests
+        // (nothing in the control logic reads the model before results come back) while the model thread finishes; the lane's
+        // first flush waits for it and uploads it.
+        double modelWait = 0;
+        auto uploadModel = [&]() -> std::string {
+            auto w0 = clk::now();
+            const bool ok = waitModel();
+            modelWait = secs(w0, clk::now());
+            if (!ok) return "the model could not be learned";      // (the main thread reports why)
+            FbModel fm{};
+            fm.max_read_len = model.maxReadLength; fm.err_pos = model.errorPosDist.data(); fm.ins_pos = model.inPosDist.data(); fm.del_pos = model.delPosDist.data();
+            for (int i = 0; i < 5; i++) for (int j = 0; j < 5; j++) fm.err_type[i * 5 + j] = model.errorTypeProbs[i][j];
+            fm.n_insert = model.maxInsertSize; fm.insert_pdf = model.insertPdfSmoothed.data();
+            fm.insert_min = model.insertThresholdMin; fm.insert_max = model.insertThresholdMax; fm.prob_cutoff = model.gapProbCutOff;
+            if (fb_model_upload(ctx, &fm) != FB_OK) return std::string("fb_model_upload: ") + fb_last_error(ctx);
+            return std::string();
+        };
 
         auto d1 = clk::now();
         devCtx[d] = secs(d0, d1);
@@ -482,7 +499,7 @@ int fillgapsMain(int argc, const char* const* argv) {
         if (const char* e = getenv("FIGBIRD_LANE_WORKERS")) nWorkers = std::max(1, atoi(e));
         nWorkers = std::max(1, std::min(nWorkers, (int)mine.size()));
         const int cap = std::max(1, (std::min((int)mine.size(), inflight) + nWorkers - 1) / nWorkers);
-        LaneQueue q(ctx, nWorkers);
+        LaneQueue q(ctx, nWorkers, uploadModel);
         LaneWork lw; lw.mine = &mine; lw.fills = &fills; lw.results = &results;
         std::vector<std::thread> th;
         std::atomic<long long> cpuNs(0);
@@ -494,6 +511,7 @@ int fillgapsMain(int argc, const char* const* argv) {
         if (!lw.error.empty()) devErr[d] = lw.error;
         if (!devErr[d].empty()) { fb_ctx_destroy(ctx); return; }      // a CUDA error is sticky: never pool a context that has failed
         devWork[d] = secs(d1, clk::now()); devCpu[d] = cpuNs.load() * 1e-9;
+        devCtx[d] += modelWait;      // (t_ctx_upload keeps its meaning: context, batch upload and the wait for the model)
         {   // this run's share of the context's cumulative counters
             FbCounters c1{}; fb_get_counters(ctx, &c1);
             c1.placements_p1 -= ctr0.placements_p1; c1.placements_p2 -= ctr0.placements_p2; c1.base_terms -= ctr0.base_terms; c1.kernel_launches -= ctr0.kernel_launches;
@@ -520,8 +538,12 @@ int fillgapsMain(int argc, const char* const* argv) {
             if (fd < 0) return;
             std::vector<int> seq;
             { const char* e = getenv("FIGBIRD_DRAW_ORDER"); if (!(e && !strcmp(e, "gap"))) seq = referenceDrawOrder(a.tmpDir, totGaps, a.numThreads); }
-            { std::vector<int> keep; std::vector<char> seen(results.size(), 0); for (int g : seq) if (g >= 0 && (size_t)g < results.size() && !seen[(size_t)g]) { seen[(size_t)g] = 1; keep.push_back(g); }
-              for (size_t g = 0; g < results.size(); g++) if (!seen[g]) keep.push_back((int)g); seq.swap(keep); }
+            {   // a permutation of the gaps that have a result, whatever the dealing said (gap order for anything it left out)
+                std::vector<int> keep; std::vector<char> seen(results.size(), 0);
+                for (int g : seq) if (g >= 0 && (size_t)g < results.size() && !seen[(size_t)g]) { seen[(size_t)g] = 1; keep.push_back(g); }
+                for (size_t g = 0; g < results.size(); g++) if (!seen[g]) keep.push_back((int)g);
+                seq.swap(keep);
+            }
             std::vector<size_t> off(results.size() + 1, 0);
             for (size_t i = 0; i < results.size(); i++) off[i + 1] = off[i] + results[(size_t)seq[i]].drawText.size();
             const size_t total = off[results.size()];
