@@ -1,6 +1,7 @@
-"""One process per GPU: rank discovery and the only cross-rank step of the path -- summing / maximising the
-per-rank counters of a run.  Gaps are independent, so nothing else is exchanged: every rank
-fills its own shard, and the host that wants whole-job figures reduces a handful of scalars."""
+"""bench.py under torchrun (one process per GPU): rank discovery and the only cross-rank step -- the maximum / sum of a handful of
+per-rank scalars (the wall time of the timed steps).  Gaps are independent, so nothing is exchanged on the data path:
+rank 0 drives fb_fillgaps_main over all GPUs of the box (the product's own cost-balanced sharding, fb_fillgaps.cpp), the other
+ranks hold their GPU's place in the job and meet rank 0 at host-side barriers."""
 import os
 
 
@@ -20,15 +21,3 @@ def reduce_counters(values, dist=None, device="cpu"):
     mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
     return dict(zip(keys, mx.tolist())), dict(zip(keys, sm.tolist()))
-
-
-def shard_gaps(costs, world):
-    """Longest-processing-time-first assignment of gaps to ranks by cost estimate (the same rule fb_fillgaps_main uses
-    for the GPUs of one process, fb_fillgaps.cpp): returns a list of gap-index lists, one per rank."""
-    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
-    load = [0.0] * world
-    out = [[] for _ in range(world)]
-    for g in order:
-        r = min(range(world), key=lambda k: (load[k], k))
-        out[r].append(g); load[r] += costs[g] + 1
-    return out
