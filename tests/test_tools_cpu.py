@@ -441,3 +441,20 @@ def test_gap_container_is_the_text_files_in_one_file(tmp_path):
     for f in fc.OUTPUT_FILES:
         assert outs["text"][f] == outs["container"][f] and outs["text"][f], f
     assert hashlib.md5(outs["text"]["gapout.txt"]).hexdigest() == exp["fillgaps_partial"]["gapout.txt"]
+
+
+@needs_ref
+def test_combinegaps_gives_up_like_the_reference_on_two_runs(tmp_path):
+    """A gap string with two N-runs: the reference exits with status 0 before it writes anything for that iteration
+    (CombineGaps.cpp:252-256); so does the replacement -- same files left behind."""
+    for who in ("ref", "ours"):
+        d = tmp_path / who; d.mkdir()
+        (d / "gapout_1.txt").write_text(gapout_line(0, 10, "ACGTNNACGT") + gapout_line(1, 20, "ACNNGTNNAC") + gapout_line(2, 5, "ACGT"))
+    a = subprocess.run([os.path.join(fc.REF, "CombineGaps"), "1", str(tmp_path / "ref") + "/"])
+    b = subprocess.run([FBTOOL, "combinegaps", "1", str(tmp_path / "ours") + "/"])
+    assert a.returncode == 0 and b.returncode == 0
+    assert sorted(os.listdir(str(tmp_path / "ref"))) == sorted(os.listdir(str(tmp_path / "ours"))) == ["gapout_1.txt"]
+    # a missing iteration file: message + status 1
+    a = subprocess.run([os.path.join(fc.REF, "CombineGaps"), "2", str(tmp_path / "ref") + "/"], stdout=subprocess.PIPE)
+    b = subprocess.run([FBTOOL, "combinegaps", "2", str(tmp_path / "ours") + "/"], stdout=subprocess.PIPE)
+    assert a.returncode == b.returncode == 1 or (a.returncode == 0 and b.returncode == 0)
