@@ -275,13 +275,16 @@ static std::vector<LaneSpec> visibleLanes() {
 // gaps in ascending order (writeGapLoad :313-334, Figbird.cpp:7283-7317) and the workers' files are concatenated in worker order
 // (mergeFiles :222-258).  The sort of the workers by remaining room is std::sort with the reference's comparator on the
 // reference's container, i.e. the same unstable order for equal keys.
-static std::vector<int> referenceDrawOrder(const std::string& tmpDir, int totGaps, int numThreads) {
+// firstWorker = how many entries at the front of the order belong to worker 0, workers = number of worker files that are merged.
+static std::vector<int> referenceDrawOrder(const std::string& tmpDir, int totGaps, int numThreads, int& firstWorker, int& workers) {
     std::vector<int> order;
+    firstWorker = 0; workers = 1;
     if (totGaps <= 0) return order;
     int T = numThreads;
     std::vector<std::vector<int>> alloc;
-    if (totGaps <= T || T < 1) {
+    if (totGaps <= T || T < 1) {      // one gap per worker (FillGaps.cpp:460-464, 497-505)
         for (int i = 0; i < totGaps; i++) order.push_back(i);
+        firstWorker = 1; workers = T < 1 ? 1 : totGaps;
         return order;
     }
     const float tf = (float)(totGaps * 1.0 / T);
@@ -314,6 +317,7 @@ static std::vector<int> referenceDrawOrder(const std::string& tmpDir, int totGap
             for (int j = 0; j < rem[(size_t)i][1] && k < nLarge; j++) alloc[(size_t)rem[(size_t)i][0]].push_back(large[(size_t)k++]);
     }
     for (auto& a : alloc) { std::sort(a.begin(), a.end()); for (int g : a) order.push_back(g); }
+    firstWorker = (int)alloc[0].size(); workers = T;
     return order;
 }
 
@@ -537,7 +541,16 @@ int fillgapsMain(int argc, const char* const* argv) {
             const int fd = open((a.tmpDir + "draw.txt").c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
             if (fd < 0) return;
             std::vector<int> seq;
-            { const char* e = getenv("FIGBIRD_DRAW_ORDER"); if (!(e && !strcmp(e, "gap"))) seq = referenceDrawOrder(a.tmpDir, totGaps, a.numThreads); }
+            int firstWorker = 0, workers = 1;
+            { const char* e = getenv("FIGBIRD_DRAW_ORDER"); if (!(e && !strcmp(e, "gap"))) seq = referenceDrawOrder(a.tmpDir, totGaps, a.numThreads, firstWorker, workers); }
+            // mergeFiles (FillGaps.cpp:222-258) appends worker i's file with `out << a.rdbuf() << b.rdbuf()`: inserting an EMPTY a.rdbuf()
+            // sets failbit on `out`, b is then dropped, and the merged file stays empty from there on -- so when worker 0 drew nothing
+            // and there is more than one worker, the reference's draw.txt is empty.  Reproduced.
+            if (workers >= 2 && !seq.empty()) {
+                size_t first = 0;
+                for (int i = 0; i < firstWorker && i < (int)seq.size(); i++) if (seq[(size_t)i] >= 0 && (size_t)seq[(size_t)i] < results.size()) first += results[(size_t)seq[(size_t)i]].drawText.size();
+                if (first == 0) { close(fd); return; }
+            }
             {   // a permutation of the gaps that have a result, whatever the dealing said (gap order for anything it left out)
                 std::vector<int> keep; std::vector<char> seen(results.size(), 0);
                 for (int g : seq) if (g >= 0 && (size_t)g < results.size() && !seen[(size_t)g]) { seen[(size_t)g] = 1; keep.push_back(g); }
