@@ -317,8 +317,13 @@ bool writeFilledContigs(const std::string& tmpDir, const Scaffolds& sc, const st
             if (nStart == 0 && !(gapCount >= 0 && gapCount < (int)gtf.size() && gtf[gapCount] > 0)) {
                 // a run of ordinary bases outside any gap and past the trimmed flank: copied in one piece (the last base of
                 // the scaffold and anything from the next N on take the per-character path below)
-                size_t k = j;
-                while (k + 1 < s.size() && s[k] != 'N' && s[k] != 'n') k++;
+                // k = the next N / n at or after j, at most the last base (memchr: this loop is 100 Mbp of a C4 draft)
+                size_t k = s.size() - 1;
+                if (j < k) {
+                    const char* b = s.data();
+                    if (const void* pN = memchr(b + j, 'N', k - j)) k = (size_t)((const char*)pN - b);
+                    if (const void* pn = memchr(b + j, 'n', k - j)) k = (size_t)((const char*)pn - b);
+                } else k = j;
                 if (k > j) { buf.append(s, j, k - j); j = k - 1; continue; }
             }
             bool isN = (s[j] == 'N' || s[j] == 'n');
