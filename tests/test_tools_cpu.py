@@ -14,6 +14,7 @@ import random
 import re
 import shutil
 import subprocess
+import sys
 import tarfile
 
 import pytest
@@ -254,8 +255,9 @@ def gapout_line(i, og, s):
 
 
 @needs_ref
-def test_combinegaps_matches_reference(tmp_path):
-    rng = random.Random(9)
+@pytest.mark.parametrize("seed", [9, 10, 11, 12])
+def test_combinegaps_matches_reference(tmp_path, seed):
+    rng = random.Random(seed)
     # iteration 1: closed gaps, gaps that keep one N-run, a gap closed with length 0; later iterations only list the open ones
     state = []
     it1 = []
@@ -458,3 +460,12 @@ def test_combinegaps_gives_up_like_the_reference_on_two_runs(tmp_path):
     a = subprocess.run([os.path.join(fc.REF, "CombineGaps"), "2", str(tmp_path / "ref") + "/"], stdout=subprocess.PIPE)
     b = subprocess.run([FBTOOL, "combinegaps", "2", str(tmp_path / "ours") + "/"], stdout=subprocess.PIPE)
     assert a.returncode == b.returncode == 1 or (a.returncode == 0 and b.returncode == 0)
+
+
+@needs_ref
+def test_preprocess_differential_fuzz_smoke():
+    """Two rounds of tools/fuzz_preprocess.py (random bowtie2-plausible edits of every pairing class, both modes, maxDistance below and
+    above 250, block / sequential paths); the tool itself runs as many rounds as one likes (46 rounds were identical when this was
+    written)."""
+    p = subprocess.run([sys.executable, os.path.join(os.path.dirname(HERE), "tools", "fuzz_preprocess.py"), "2", "3"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
+    assert p.returncode == 0 and p.stdout.decode().count("identical") == 2, p.stdout.decode()[-2000:]
