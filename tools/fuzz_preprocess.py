@@ -2,7 +2,8 @@
 """Differential fuzzing of fb_preprocess_main against the reference Preprocess (oracle/_ref): the SAM of the pp1 fixture with random,
 bowtie2-plausible edits per pair (flags of every pairing class, strands, positions moved next to gaps, CIGARs with soft clips /
 insertions / deletions, mates on another scaffold, N-rich reads, duplicates), both modes, several maxDistance values.
-usage: tools/fuzz_preprocess.py [rounds] [seed]     -> prints one line per round, exits 1 on the first difference (inputs kept)."""
+usage: tools/fuzz_preprocess.py [rounds] [seed]     -> prints one line per round, exits 1 on the first difference (inputs kept).
+FUZZ_MULTI=1 also repeats alignment lines (several alignments per read, as bowtie2 -k would write them)."""
 import os
 import random
 import shutil
@@ -77,6 +78,11 @@ def mutate(rng, lines, gaps, ncontig):
             if not (int(f[1]) & 4) and not any(t.startswith("MD:Z:") for t in f[11:]):
                 f.append("MD:Z:%d" % len(f[9]))
         out += ["\t".join(a), "\t".join(b)]
+        if os.environ.get("FUZZ_MULTI") and rng.random() < 0.04:      # several alignment lines per read (bowtie2 -k): the sequential path
+            if int(a[1]) & 2:
+                out += ["\t".join(a), "\t".join(b)]
+            else:
+                out.insert(len(out) - 1, "\t".join(a[:3] + [str(max(1, int(a[3]) + rng.randrange(-300, 300)))] + a[4:]))
     return out
 
 
